@@ -1,0 +1,756 @@
+// ace_b200.cu -- C ABI (include/ace_b200.h) of the B200-native ACE hot path: device-resident fit
+// handle + per-function entry points.  Host code here only sequences kernels; all arithmetic of the
+// path runs in the hand-written sm_100a kernels of dgemm_nt.cuh / chol.cuh / gp_kernels.cuh /
+// pred_kernels.cuh.  No cuBLAS / cuSOLVER, no CPU fallback.
+#include "../../include/ace_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "chol.cuh"
+#include "gp_kernels.cuh"
+#include "pred_kernels.cuh"
+
+namespace ace {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+static int usage(const std::string& m) {
+  set_error(m);
+  return ACE_ERR_USAGE;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------------
+// small RAII device buffer
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct DBuf {
+  T* p = nullptr;
+  size_t count = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { release(); }
+  int alloc(size_t n) {
+    release();
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error(std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
+      return -(int)e - 1000;
+    }
+    count = n;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    count = 0;
+  }
+};
+
+static int check_device() {
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt <= 0) {
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+              "); this library has no CPU fallback");
+    return ACE_ERR_NO_DEVICE;
+  }
+  return 0;
+}
+
+static int configure_kernels_once() {
+  // per device: opt in to large dynamic shared memory for every kernel that needs it
+  static std::mutex mu;
+  static std::vector<int> done;
+  int dev = 0;
+  ACE_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (std::find(done.begin(), done.end(), dev) != done.end()) return 0;
+  ACE_TRY(configure_dense_kernels());
+  done.push_back(dev);
+  return 0;
+}
+
+// host (ld = rows) -> device (ld = ld_dev), zero padded
+static int upload_matrix(double* dst, long ld_dev, int rows_pad, const double* src, int rows, int cols,
+                         cudaStream_t st) {
+  ACE_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)ld_dev * (size_t)std::max(cols, 1), st));
+  (void)rows_pad;
+  if (rows > 0 && cols > 0)
+    ACE_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * ld_dev, src, sizeof(double) * rows, sizeof(double) * rows,
+                               cols, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+static int download_matrix(double* dst, int rows, int cols, const double* src, long ld_dev, cudaStream_t st) {
+  if (rows > 0 && cols > 0)
+    ACE_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * rows, src, sizeof(double) * ld_dev, sizeof(double) * rows,
+                               cols, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+__global__ void pad_identity_kernel(double* A, long ld, int n, int n_pad) {
+  // rows/cols >= n of a freshly uploaded (zero padded) matrix become an identity block
+  const int i = n + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) A[i + (size_t)i * ld] = 1.0;
+}
+
+__global__ void add_diag_kernel(double* A, long ld, int n, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i + (size_t)i * ld] += v;
+}
+
+__global__ void synth_spd_kernel(double* A, long ld, int n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * n) return;
+  const int i = (int)(idx % n), j = (int)(idx / n);
+  const double t = 8.0 * (double)(i - j) / (double)n;
+  A[i + (size_t)j * ld] = exp(-t * t) + (i == j ? 0.5 : 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------------
+template <int BMAX>
+static int launch_kernmat_b(const KernArgs& a, int kind, size_t smem, unsigned grid, cudaStream_t st) {
+  if (kind == 0) {
+    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<BMAX, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernmat_kernel<BMAX, 0><<<grid, 256, smem, st>>>(a);
+  } else {
+    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<BMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernmat_kernel<BMAX, 1><<<grid, 256, smem, st>>>(a);
+  }
+  ACE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_kernmat(const KernArgs& a, int kind, cudaStream_t st) {
+  const int B = a.B;
+  if (B < 1 || B > BMAXT || a.p < 1 || a.p > PMAX) {
+    set_error("kernel build supports 1 <= p <= 64 and B = Bz+1 <= 32");
+    return ACE_ERR_UNSUPPORTED;
+  }
+  const int bmax = B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 12 ? 12 : B <= 16 ? 16 : 32;
+  const size_t smem = kb::smem_bytes(a.p, B - 1, bmax, a.sym != 0);
+  if (smem > 227 * 1024) {
+    set_error("kernel build: p and Bz too large for one shared-memory tile");
+    return ACE_ERR_UNSUPPORTED;
+  }
+  unsigned grid;
+  if (a.sym) {
+    const long T = a.n1_pad / kb::T;
+    grid = (unsigned)(T * (T + 1) / 2);
+  } else {
+    grid = (unsigned)((a.n1_pad / kb::T) * (a.n2_pad / kb::T));
+  }
+  switch (bmax) {
+    case 2: return launch_kernmat_b<2>(a, kind, smem, grid, st);
+    case 4: return launch_kernmat_b<4>(a, kind, smem, grid, st);
+    case 8: return launch_kernmat_b<8>(a, kind, smem, grid, st);
+    case 12: return launch_kernmat_b<12>(a, kind, smem, grid, st);
+    case 16: return launch_kernmat_b<16>(a, kind, smem, grid, st);
+    default: return launch_kernmat_b<32>(a, kind, smem, grid, st);
+  }
+}
+
+struct GradPlan {
+  int PD = 0, BT = 0, groups = 0, gy = 0, threads = 0, gx = 0;
+  size_t smem = 0;
+};
+
+static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
+  static const int table[][2] = {{4, 16}, {8, 8}, {12, 5}, {16, 4}, {20, 3}, {24, 2}, {32, 2}, {48, 1}, {64, 1}};
+  for (auto& t : table) {
+    if (p <= t[0]) {
+      pl->PD = t[0];
+      pl->BT = t[1];
+      break;
+    }
+  }
+  if (pl->PD == 0 || B > BMAXT) {
+    set_error("gradient pass supports p <= 64 and B <= 32");
+    return ACE_ERR_UNSUPPORTED;
+  }
+  pl->groups = (B + pl->BT - 1) / pl->BT;
+  pl->gy = (pl->groups + gk::GROUPS_PER_CTA - 1) / gk::GROUPS_PER_CTA;
+  const int gpc = std::min(pl->groups, gk::GROUPS_PER_CTA);
+  pl->threads = 64 * gpc;
+  pl->smem = gk::smem_bytes(pl->PD, B - 1, pl->BT, kind);
+  if (pl->smem > 227 * 1024) {
+    set_error("gradient pass: p and Bz too large for one shared-memory tile");
+    return ACE_ERR_UNSUPPORTED;
+  }
+  pl->gx = 2 * sms;
+  return 0;
+}
+
+template <int PD, int BT>
+static int launch_grad_t(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
+  dim3 grid(pl.gx, pl.gy);
+  if (kind == 0) {
+    ACE_CUDA(cudaFuncSetAttribute(grad_kernel<PD, BT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    grad_kernel<PD, BT, 0><<<grid, pl.threads, pl.smem, st>>>(a);
+  } else {
+    ACE_CUDA(cudaFuncSetAttribute(grad_kernel<PD, BT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    grad_kernel<PD, BT, 1><<<grid, pl.threads, pl.smem, st>>>(a);
+  }
+  ACE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
+  switch (pl.PD) {
+    case 4: return launch_grad_t<4, 16>(a, kind, pl, st);
+    case 8: return launch_grad_t<8, 8>(a, kind, pl, st);
+    case 12: return launch_grad_t<12, 5>(a, kind, pl, st);
+    case 16: return launch_grad_t<16, 4>(a, kind, pl, st);
+    case 20: return launch_grad_t<20, 3>(a, kind, pl, st);
+    case 24: return launch_grad_t<24, 2>(a, kind, pl, st);
+    case 32: return launch_grad_t<32, 2>(a, kind, pl, st);
+    case 48: return launch_grad_t<48, 1>(a, kind, pl, st);
+    default: return launch_grad_t<64, 1>(a, kind, pl, st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Core: everything a GP step needs on one device.  Used by the fit handle and, transiently, by the
+// per-function entry points.
+// ---------------------------------------------------------------------------------------------
+struct Core {
+  int device = 0, sms = 148;
+  int n = 0, n_pad = 0, p = 0, Bz = 0, B = 0, P = 0, kind = 0;
+  cudaStream_t st = nullptr, side = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t tev[8] = {};
+  DBuf<double> X, Z, LZ, y, theta, m, v, grad, tab, sc, A, Bf, DX, DU, dvec, alpha, uvec, svec, Ka, pu, ps, partials;
+  DBuf<int> info;
+  double* h_sc = nullptr;  // pinned: SC_COUNT doubles + info
+  GradPlan gp;
+  int nchunks = 0;
+
+  ~Core() {
+    if (h_sc) cudaFreeHost(h_sc);
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : tev)
+      if (e) cudaEventDestroy(e);
+    if (st) cudaStreamDestroy(st);
+    if (side) cudaStreamDestroy(side);
+  }
+
+  int init(int dev, int n_, int p_, int Bz_, int kind_, bool need_dense, bool need_grad) {
+    ACE_TRY(check_device());
+    device = dev;
+    ACE_CUDA(cudaSetDevice(dev));
+    ACE_TRY(configure_kernels_once());
+    cudaDeviceProp prop;
+    ACE_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) {
+      set_error("this library is built for sm_100a (B200) only");
+      return ACE_ERR_NO_DEVICE;
+    }
+    sms = prop.multiProcessorCount;
+    n = n_; p = p_; Bz = Bz_; B = Bz_ + 1; P = 2 + B + B * p; kind = kind_;
+    n_pad = round_up(n, TB);
+    ACE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int lo = 0, hi = 0;
+    ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ACE_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));  // panel stream: high priority
+    for (auto& e : ev) ACE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : tev) ACE_CUDA(cudaEventCreate(&e));
+    ACE_CUDA(cudaMallocHost(&h_sc, sizeof(double) * (SC_COUNT + 2)));
+    const size_t N = (size_t)n_pad;
+    ACE_TRY(X.alloc(N * p));
+    ACE_TRY(Z.alloc(N * std::max(Bz, 1)));
+    ACE_TRY(LZ.alloc(N * std::max(Bz, 1)));
+    ACE_TRY(y.alloc(N));
+    ACE_TRY(theta.alloc(P));
+    ACE_TRY(m.alloc(P));
+    ACE_TRY(v.alloc(P));
+    ACE_TRY(grad.alloc(P));
+    ACE_TRY(tab.alloc(TAB_SIZE));
+    ACE_TRY(sc.alloc(SC_COUNT));
+    ACE_TRY(info.alloc(1));
+    ACE_CUDA(cudaMemsetAsync(sc.p, 0, sizeof(double) * SC_COUNT, st));
+    ACE_CUDA(cudaMemsetAsync(m.p, 0, sizeof(double) * P, st));
+    ACE_CUDA(cudaMemsetAsync(v.p, 0, sizeof(double) * P, st));
+    ACE_CUDA(cudaMemsetAsync(grad.p, 0, sizeof(double) * P, st));
+    ACE_CUDA(cudaMemsetAsync(info.p, 0, sizeof(int), st));
+    if (need_dense) {
+      ACE_TRY(A.alloc(N * N));
+      ACE_TRY(Bf.alloc(N * N));
+      ACE_TRY(DX.alloc(N * TB));
+      ACE_TRY(DU.alloc(N * TB));
+      ACE_TRY(dvec.alloc(N));
+    }
+    if (need_grad) {
+      ACE_TRY(plan_grad(p, B, kind, sms, &gp));
+      nchunks = (n + gv::CHUNK - 1) / gv::CHUNK;
+      ACE_TRY(alpha.alloc(N));
+      ACE_TRY(uvec.alloc(N));
+      ACE_TRY(svec.alloc(N));
+      ACE_TRY(Ka.alloc(N));
+      ACE_TRY(pu.alloc(N * nchunks));
+      ACE_TRY(ps.alloc(N * nchunks));
+      ACE_TRY(partials.alloc((size_t)gp.gx * gp.gy * P));
+      if (!dvec.p) ACE_TRY(dvec.alloc(N));
+    }
+    return 0;
+  }
+
+  int upload_data(const double* hy, const double* hX, const double* hZ) {
+    if (hX) ACE_TRY(upload_matrix(X.p, n_pad, n_pad, hX, n, p, st));
+    if (hZ) {
+      ACE_TRY(upload_matrix(Z.p, n_pad, n_pad, hZ, n, Bz, st));
+      const size_t cnt = (size_t)n_pad * Bz;
+      if (cnt) logabs_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(Z.p, LZ.p, cnt);
+      ACE_CUDA(cudaGetLastError());
+    }
+    if (hy) ACE_TRY(upload_matrix(y.p, n_pad, n_pad, hy, n, 1, st));
+    return 0;
+  }
+
+  int upload_theta(const double* hpar) {
+    ACE_CUDA(cudaMemcpyAsync(theta.p, hpar, sizeof(double) * P, cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+
+  DenseWork dense(double* Abuf, double* Bbuf) {
+    DenseWork w;
+    w.A = Abuf; w.ld = n_pad; w.nb = n_pad / TB; w.DX = DX.p; w.DU = DU.p; w.dvec = dvec.p; w.info = info.p;
+    w.Bf = Bbuf; w.main = st; w.side = side;
+    w.ev_panel[0] = ev[0]; w.ev_panel[1] = ev[1]; w.ev_upd[0] = ev[2]; w.ev_upd[1] = ev[3];
+    return w;
+  }
+
+  int enqueue_prep() {
+    prep_tables_kernel<<<1, 256, 0, st>>>(theta.p, p, B, tab.p);
+    ACE_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  // K (+ e^sigma on the diagonal, identity padding) of the training points into `out`
+  int enqueue_build_sym(double* out, int add_noise, double* cube, long cube_slice) {
+    KernArgs a{};
+    a.X1 = a.X2 = X.p; a.Z1 = a.Z2 = Z.p; a.LZ1 = a.LZ2 = LZ.p; a.ld1 = a.ld2 = n_pad;
+    a.n1 = a.n2 = n; a.n1_pad = a.n2_pad = n_pad; a.p = p; a.B = B; a.tab = tab.p;
+    a.K = out; a.ldk = n_pad; a.cube = cube; a.cube_slice = cube_slice;
+    a.sym = 1; a.add_noise = add_noise; a.pad_identity = add_noise;
+    return launch_kernmat(a, kind, st);
+  }
+
+  // u = Kinv y, s = Kinv 1, alpha = u - mu s (mu closed form first when asked and iter == 1)
+  int enqueue_alpha(const double* Kinv, int set_mu_first_iter) {
+    dim3 grid((n_pad + gv::ROWS - 1) / gv::ROWS, nchunks);
+    gemv2_kernel<<<grid, gv::ROWS, 0, st>>>(Kinv, n_pad, n, y.p, pu.p, ps.p, n_pad);
+    ACE_CUDA(cudaGetLastError());
+    alpha_kernel<<<1, 1024, 0, st>>>(pu.p, ps.p, nchunks, n, n_pad, theta.p, uvec.p, svec.p, alpha.p, Ka.p, sc.p,
+                                     set_mu_first_iter);
+    ACE_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  int enqueue_grad(const double* Kinv) {
+    GradArgs g{};
+    g.X = X.p; g.Z = Z.p; g.LZ = LZ.p; g.ldx = n_pad; g.Kinv = Kinv; g.ld = n_pad; g.alpha = alpha.p; g.Ka = Ka.p;
+    g.tab = tab.p; g.partials = partials.p; g.n = n; g.p = p; g.B = B; g.P = P;
+    g.ntiles_side = (n + gk::T - 1) / gk::T;
+    return launch_grad(g, kind, gp, st);
+  }
+
+  int enqueue_finalize(const double* Kinv, const ace_fit_config& c, int do_update) {
+    FinalizeArgs f{};
+    f.partials = partials.p; f.nparts = gp.gx * gp.gy; f.y = y.p; f.alpha = alpha.p; f.Ka = Ka.p; f.dvec = dvec.p;
+    f.Kinv = Kinv; f.ld = n_pad; f.tab = tab.p; f.theta = theta.p; f.m = m.p; f.v = v.p; f.grad = grad.p; f.sc = sc.p;
+    f.n = n; f.p = p; f.B = B; f.P = P; f.kind = kind; f.optimizer = c.optimizer; f.lr = c.learning_rate;
+    f.beta1 = c.beta1; f.beta2 = c.beta2; f.eps = 1e-8; f.momentum = c.momentum; f.std_y = c.std_y;
+    f.clip_at = c.clip_at; f.norm_clip = c.norm_clip; f.do_update = do_update;
+    finalize_kernel<<<1, 1024, 0, st>>>(f);
+    ACE_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  int fetch_scalars() {
+    ACE_CUDA(cudaMemcpyAsync(h_sc, sc.p, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, st));
+    ACE_CUDA(cudaMemcpyAsync(h_sc + SC_COUNT, info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ACE_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  int h_info() const { return *reinterpret_cast<const int*>(h_sc + SC_COUNT); }
+};
+
+}  // namespace ace
+
+using namespace ace;
+
+// =============================================================================================
+// fit handle
+// =============================================================================================
+struct ace_fit {
+  Core c;
+  ace_fit_config cfg;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  double iter_dev = 0.0;  // host shadow of sc[SC_ITER]
+  double ms[6] = {0, 0, 0, 0, 0, 0};
+  ~ace_fit() {
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+
+static int enqueue_iteration(ace_fit* f, bool timed) {
+  Core& c = f->c;
+  DenseWork w = c.dense(c.A.p, c.Bf.p);
+  if (timed) ACE_CUDA(cudaEventRecord(c.tev[0], c.st));
+  ACE_TRY(c.enqueue_prep());
+  ACE_TRY(c.enqueue_build_sym(c.A.p, 1, nullptr, 0));
+  if (timed) ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
+  ACE_TRY(potrf_blocked(w));
+  if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
+  ACE_TRY(trtri_merge(w));
+  if (timed) ACE_CUDA(cudaEventRecord(c.tev[3], c.st));
+  ACE_TRY(uut_inverse(w));
+  if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));
+  ACE_TRY(c.enqueue_alpha(c.Bf.p, 1));
+  ACE_TRY(c.enqueue_grad(c.Bf.p));
+  ACE_TRY(c.enqueue_finalize(c.Bf.p, f->cfg, 1));
+  if (timed) ACE_CUDA(cudaEventRecord(c.tev[5], c.st));
+  return 0;
+}
+
+extern "C" {
+
+const char* ace_last_error(void) { return g_err.c_str(); }
+const char* ace_version(void) { return "ace_b200 0.1 (sm_100a; FP64 DMMA; TMA bulk)"; }
+
+int ace_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return cnt;
+}
+
+static thread_local int g_device = 0;
+int ace_set_device(int device) {
+  ACE_TRY(check_device());
+  ACE_CUDA(cudaSetDevice(device));
+  g_device = device;
+  return 0;
+}
+
+void ace_fit_default_config(ace_fit_config* cfg) {
+  cfg->kernel = ACE_KERNEL_SE;
+  cfg->optimizer = ACE_OPT_NADAM;
+  cfg->learning_rate = 0.01;
+  cfg->beta1 = 0.9;
+  cfg->beta2 = 0.999;
+  cfg->momentum = 0.0;
+  cfg->norm_clip = 1;
+  cfg->clip_at = 1.0;
+  cfg->std_y = 1.0;
+  cfg->device = 0;
+  cfg->use_graph = 1;
+}
+
+int ace_fit_create(ace_fit** out, const double* y, const double* X, const double* Z, int n, int p, int Bz,
+                   const double* parameters, const ace_fit_config* cfg) {
+  if (!out || !y || !X || !Z || !parameters || !cfg) return usage("ace_fit_create: null argument");
+  if (n < 1 || p < 1 || Bz < 1) return usage("ace_fit_create: need n >= 1, p >= 1, Bz >= 1");
+  *out = nullptr;
+  ace_fit* f = new (std::nothrow) ace_fit();
+  if (!f) return usage("out of host memory");
+  f->cfg = *cfg;
+  int s = f->c.init(cfg->device, n, p, Bz, cfg->kernel, true, true);
+  if (s == 0) s = f->c.upload_data(y, X, Z);
+  if (s == 0) s = f->c.upload_theta(parameters);
+  if (s == 0) {
+    cudaError_t e = cudaStreamSynchronize(f->c.st);
+    if (e != cudaSuccess) {
+      set_error(std::string("ace_fit_create: ") + cudaGetErrorString(e));
+      s = -(int)e - 1000;
+    }
+  }
+  if (s != 0) {
+    delete f;
+    return s;
+  }
+  *out = f;
+  return 0;
+}
+
+int ace_fit_destroy(ace_fit* fit) {
+  if (!fit) return 0;
+  cudaSetDevice(fit->c.device);
+  cudaDeviceSynchronize();
+  delete fit;
+  return 0;
+}
+
+int ace_fit_para_update(ace_fit* f, int iter, double* stats, double* gnorm) {
+  if (!f) return usage("null handle");
+  Core& c = f->c;
+  ACE_CUDA(cudaSetDevice(c.device));
+  if ((double)iter != f->iter_dev) {
+    c.h_sc[SC_COUNT + 1] = (double)iter;
+    ACE_CUDA(cudaMemcpyAsync(c.sc.p + SC_ITER, c.h_sc + SC_COUNT + 1, sizeof(double), cudaMemcpyHostToDevice, c.st));
+    f->iter_dev = (double)iter;
+  }
+  if (f->cfg.use_graph) {
+    if (!f->gexec) {
+      ACE_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeThreadLocal));
+      int s = enqueue_iteration(f, false);
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(c.st, &g);
+      if (s != 0) {
+        if (g) cudaGraphDestroy(g);
+        return s;
+      }
+      ACE_CUDA(e);
+      f->graph = g;
+      ACE_CUDA(cudaGraphInstantiate(&f->gexec, f->graph, 0));
+    }
+    ACE_CUDA(cudaEventRecord(c.tev[6], c.st));
+    ACE_CUDA(cudaGraphLaunch(f->gexec, c.st));
+    ACE_CUDA(cudaEventRecord(c.tev[7], c.st));
+  } else {
+    ACE_CUDA(cudaEventRecord(c.tev[6], c.st));
+    ACE_TRY(enqueue_iteration(f, true));
+    ACE_CUDA(cudaEventRecord(c.tev[7], c.st));
+  }
+  ACE_TRY(c.fetch_scalars());
+  f->iter_dev = c.h_sc[SC_ITER];
+  float t = 0;
+  ACE_CUDA(cudaEventElapsedTime(&t, c.tev[6], c.tev[7]));
+  f->ms[5] = t;
+  if (!f->cfg.use_graph) {
+    for (int k = 0; k < 5; ++k) {
+      ACE_CUDA(cudaEventElapsedTime(&t, c.tev[k], c.tev[k + 1]));
+      f->ms[k] = t;
+    }
+  }
+  if (stats) {
+    stats[0] = c.h_sc[SC_RMSE];
+    stats[1] = c.h_sc[SC_EVID];
+  }
+  if (gnorm) *gnorm = c.h_sc[SC_GNORM];
+  if (c.h_info() > 0) {
+    set_error("matrix not positive definite at pivot " + std::to_string(c.h_info()));
+    return c.h_info();
+  }
+  if (c.h_sc[SC_FINITE] == 0.0) {
+    set_error("Some gradients are not finite, NaN, or NA. Often this is due to too large learning rates.");
+    return ACE_ERR_NOT_FINITE;
+  }
+  return 0;
+}
+
+int ace_fit_run(ace_fit* f, int iter_start, int max_iter, double tol, double prev_evidence, double* stats_out,
+                int* iters_done) {
+  if (!f || !iters_done) return usage("null argument");
+  double prev = prev_evidence;
+  int done = 0;
+  for (int k = 0; k < max_iter; ++k) {
+    const int iter = iter_start + k;
+    double st[2];
+    int s = ace_fit_para_update(f, iter, st, nullptr);
+    if (s != 0) {
+      *iters_done = done;
+      return s;
+    }
+    ++done;
+    if (stats_out) {
+      stats_out[2 * k] = st[0];
+      stats_out[2 * k + 1] = st[1];
+    }
+    const double change = std::fabs(st[1] - prev);  // R/main_ace.R:221
+    prev = st[1];
+    if (change < tol && iter > 3) break;
+  }
+  *iters_done = done;
+  return 0;
+}
+
+int ace_fit_get_train_stats(ace_fit* f, double* stats) {
+  if (!f || !stats) return usage("null argument");
+  Core& c = f->c;
+  ACE_CUDA(cudaSetDevice(c.device));
+  DBuf<double> B2;  // local inverse: the stored invKmatn (c.Bf) must stay as it is (quirk Q6)
+  ACE_TRY(B2.alloc((size_t)c.n_pad * c.n_pad));
+  DenseWork w = c.dense(c.A.p, B2.p);
+  ACE_TRY(c.enqueue_prep());
+  ACE_TRY(c.enqueue_build_sym(c.A.p, 1, nullptr, 0));
+  ACE_TRY(spd_inverse(w));
+  ACE_TRY(c.enqueue_alpha(B2.p, 0));
+  ACE_TRY(c.enqueue_grad(B2.p));
+  ACE_TRY(c.enqueue_finalize(B2.p, f->cfg, 0));
+  ACE_TRY(c.fetch_scalars());
+  stats[0] = c.h_sc[SC_RMSE];
+  stats[1] = c.h_sc[SC_EVID];
+  if (c.h_info() > 0) return c.h_info();
+  return 0;
+}
+
+int ace_fit_get_parameters(ace_fit* f, double* par) {
+  if (!f || !par) return usage("null argument");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  ACE_CUDA(cudaMemcpyAsync(par, f->c.theta.p, sizeof(double) * f->c.P, cudaMemcpyDeviceToHost, f->c.st));
+  ACE_CUDA(cudaStreamSynchronize(f->c.st));
+  return 0;
+}
+
+int ace_fit_set_parameters(ace_fit* f, const double* par) {
+  if (!f || !par) return usage("null argument");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  ACE_TRY(f->c.upload_theta(par));
+  ACE_CUDA(cudaStreamSynchronize(f->c.st));
+  return 0;
+}
+
+int ace_fit_get_gradients(ace_fit* f, double* g) {
+  if (!f || !g) return usage("null argument");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  ACE_CUDA(cudaMemcpyAsync(g, f->c.grad.p, sizeof(double) * f->c.P, cudaMemcpyDeviceToHost, f->c.st));
+  ACE_CUDA(cudaStreamSynchronize(f->c.st));
+  return 0;
+}
+
+int ace_fit_get_optimizer_state(ace_fit* f, double* m, double* v) {
+  if (!f) return usage("null argument");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  if (m) ACE_CUDA(cudaMemcpyAsync(m, f->c.m.p, sizeof(double) * f->c.P, cudaMemcpyDeviceToHost, f->c.st));
+  if (v) ACE_CUDA(cudaMemcpyAsync(v, f->c.v.p, sizeof(double) * f->c.P, cudaMemcpyDeviceToHost, f->c.st));
+  ACE_CUDA(cudaStreamSynchronize(f->c.st));
+  return 0;
+}
+
+int ace_fit_get_invKmatn(ace_fit* f, double* inv) {
+  if (!f || !inv) return usage("null argument");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  ACE_TRY(download_matrix(inv, f->c.n, f->c.n, f->c.Bf.p, f->c.n_pad, f->c.st));
+  ACE_CUDA(cudaStreamSynchronize(f->c.st));
+  return 0;
+}
+
+int ace_fit_get_alpha(ace_fit* f, double* a) {
+  if (!f || !a) return usage("null argument");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  ACE_CUDA(cudaMemcpyAsync(a, f->c.alpha.p, sizeof(double) * f->c.n, cudaMemcpyDeviceToHost, f->c.st));
+  ACE_CUDA(cudaStreamSynchronize(f->c.st));
+  return 0;
+}
+
+int ace_fit_dims(ace_fit* f, int* n, int* p, int* B, int* P) {
+  if (!f) return usage("null argument");
+  if (n) *n = f->c.n;
+  if (p) *p = f->c.p;
+  if (B) *B = f->c.B;
+  if (P) *P = f->c.P;
+  return 0;
+}
+
+int ace_fit_last_timing(ace_fit* f, double* ms6) {
+  if (!f || !ms6) return usage("null argument");
+  for (int k = 0; k < 6; ++k) ms6[k] = f->ms[k];
+  return 0;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// posterior (shared by the handle and the per-function entry points)
+// =============================================================================================
+namespace ace {
+
+// T = Kx * Kinv (Kinv symmetric), then map / var rows.  Kx: nx_pad x n_pad (ld nx_pad, zero padded),
+// kdiag: nx (diag of K_xx).  noise: e^sigma added to the variance (pred_cpp) or 0 (marginal).
+struct PostOut {
+  DBuf<double> T, map, var, p1, p2;
+};
+
+static int posterior_rows(Core& c, const double* Kinv, const double* Kx, const double* kdiag, int nx, int nx_pad,
+                          double mu, double noise, PostOut& o) {
+  const int n = c.n, n_pad = c.n_pad;
+  ACE_TRY(o.T.alloc((size_t)nx_pad * n_pad));
+  GemmNT g{};
+  g.A = Kx; g.lda = nx_pad; g.B = Kinv; g.ldb = n_pad; g.C = o.T.p; g.ldc = nx_pad;
+  g.M = nx_pad; g.N = n_pad; g.K = n_pad; g.alpha = 1.0; g.beta = 0.0;
+  ACE_TRY(launch_gemm_nt(g, c.st));
+  const int chunks = (n + pk::CHUNK - 1) / pk::CHUNK;
+  ACE_TRY(o.p1.alloc((size_t)nx_pad * chunks));
+  ACE_TRY(o.p2.alloc((size_t)nx_pad * chunks));
+  ACE_TRY(o.map.alloc(nx_pad));
+  ACE_TRY(o.var.alloc(nx_pad));
+  dim3 grid((nx_pad + pk::ROWS - 1) / pk::ROWS, chunks);
+  rowdot2_kernel<<<grid, pk::ROWS, 0, c.st>>>(o.T.p, Kx, nx_pad, nx_pad, n, c.y.p, mu, o.p1.p, o.p2.p);
+  ACE_CUDA(cudaGetLastError());
+  post_finish_kernel<<<(nx_pad + 255) / 256, 256, 0, c.st>>>(o.p1.p, o.p2.p, chunks, nx, nx_pad, kdiag, noise,
+                                                            o.map.p, o.var.p);
+  ACE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ace
+
+extern "C" {
+
+int ace_fit_predict(ace_fit* f, const double* X2, const double* Z2, int nx, double mean_y, double std_y,
+                    double* map, double* ci, double* var) {
+  if (!f || !X2 || !Z2 || !map || !ci || !var || nx < 1) return usage("ace_fit_predict: bad argument");
+  Core& c = f->c;
+  ACE_CUDA(cudaSetDevice(c.device));
+  const int nx_pad = round_up(nx, TB);
+  DBuf<double> dX2, dZ2, dLZ2, Kx, kd;
+  ACE_TRY(dX2.alloc((size_t)nx_pad * c.p));
+  ACE_TRY(dZ2.alloc((size_t)nx_pad * c.Bz));
+  ACE_TRY(dLZ2.alloc((size_t)nx_pad * c.Bz));
+  ACE_TRY(Kx.alloc((size_t)nx_pad * c.n_pad));
+  ACE_TRY(kd.alloc(nx_pad));
+  ACE_TRY(upload_matrix(dX2.p, nx_pad, nx_pad, X2, nx, c.p, c.st));
+  ACE_TRY(upload_matrix(dZ2.p, nx_pad, nx_pad, Z2, nx, c.Bz, c.st));
+  logabs_kernel<<<(unsigned)(((size_t)nx_pad * c.Bz + 255) / 256), 256, 0, c.st>>>(dZ2.p, dLZ2.p, (size_t)nx_pad * c.Bz);
+  ACE_CUDA(cudaGetLastError());
+  ACE_TRY(c.enqueue_prep());  // kernels built from the CURRENT parameters (R/kernel_SE_R6.R:78-79)
+  KernArgs a{};
+  a.X1 = dX2.p; a.Z1 = dZ2.p; a.LZ1 = dLZ2.p; a.ld1 = nx_pad;
+  a.X2 = c.X.p; a.Z2 = c.Z.p; a.LZ2 = c.LZ.p; a.ld2 = c.n_pad;
+  a.n1 = nx; a.n2 = c.n; a.n1_pad = nx_pad; a.n2_pad = c.n_pad; a.p = c.p; a.B = c.B; a.tab = c.tab.p;
+  a.K = Kx.p; a.ldk = nx_pad;
+  ACE_TRY(launch_kernmat(a, c.kind, c.st));
+  kdiag_kernel<<<(nx_pad + 255) / 256, 256, 0, c.st>>>(dZ2.p, dLZ2.p, nx_pad, nx, c.B, c.kind, c.tab.p, 0, kd.p);
+  ACE_CUDA(cudaGetLastError());
+  double hpar[2];
+  ACE_CUDA(cudaMemcpyAsync(hpar, c.theta.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c.st));
+  ACE_CUDA(cudaStreamSynchronize(c.st));
+  PostOut o;
+  ACE_TRY(posterior_rows(c, c.Bf.p, Kx.p, kd.p, nx, nx_pad, hpar[1], std::exp(hpar[0]), o));
+  std::vector<double> hm(nx), hv(nx);
+  ACE_CUDA(cudaMemcpyAsync(hm.data(), o.map.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));
+  ACE_CUDA(cudaMemcpyAsync(hv.data(), o.var.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));
+  ACE_CUDA(cudaStreamSynchronize(c.st));
+  for (int i = 0; i < nx; ++i) {  // src/pred_cpp.cpp:20,26-29
+    map[i] = mean_y + std_y * (hm[i] + hpar[1]);
+    const double sd = std_y * std::sqrt(std::fabs(hv[i]));
+    ci[i] = map[i] - 1.96 * sd;
+    ci[i + nx] = map[i] + 1.96 * sd;
+    var[i] = sd * sd;
+  }
+  return 0;
+}
+
+}  // extern "C"
+
+#include "api_functions.inl"

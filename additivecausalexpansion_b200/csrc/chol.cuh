@@ -1,0 +1,434 @@
+// chol.cuh -- blocked FP64 Cholesky, triangular inverse and SPD inverse on the 128-block grid.
+//
+// Replaces invkernel_cpp's eigendecomposition route (src/kernel_SE_cpp.cpp:137-157:
+// K + e^sigma I = V L V', inv = (V L^-1/2)(V L^-1/2)', logdet = sum log lambda) by
+//   phase 1  potrf   A = L L'            right-looking, panel width 512 with one-panel look-ahead
+//   phase 2  trtri   U = L^-T            bottom-up pairwise merge, strided-batched per level
+//   phase 3  U U'    (K + e^sigma I)^-1  ONE triangular SYRK launch, mirrored on the fly
+// with logdet = 2 sum log L_ii.  Every O(n^3) flop runs in dgemm_nt_kernel (DMMA); the only other
+// kernels are the two 128-wide leaf kernels below.  n^3 flops in total (n^3/3 per phase).
+//
+// Storage (column-major, ld = n_pad, n_pad a multiple of 128, padding = identity):
+//   lower(A)  : L, later X = L^-1 (needed as operands while merging)
+//   upper(A)  : U = L^-T (strictly-upper 128-blocks)
+//   DX, DU    : dense 128x128 tiles holding the diagonal blocks of X (lower) and U (upper)
+//   dvec      : diag(L)
+//   Bf        : workspace during phase 2, receives the full symmetric inverse in phase 3
+#pragma once
+#include "dgemm_nt.cuh"
+
+namespace ace {
+
+// ---------------------------------------------------------------------------------------------
+// Leaf: Cholesky of one 128x128 diagonal tile + inverse of its factor, one CTA.
+// The tile lives in registers (16x16 threads, cyclic 8x8 elements each); one __syncthreads per
+// column thanks to double-buffered pivot columns/rows.
+// ---------------------------------------------------------------------------------------------
+namespace leaf {
+constexpr int LD = 129;
+constexpr size_t SMEM_BYTES = (size_t)(128 * LD + 2 * 128 + 2 * 128 + 128 + 128) * 8;
+}  // namespace leaf
+
+template <int JB>
+__device__ __forceinline__ void leaf_chol_block(double (&r)[8][8], double* Ls, double* colbuf, double* dg,
+                                                int tx, int ty, int* info, int blk) {
+  using namespace leaf;
+#pragma unroll 1
+  for (int jx = 0; jx < 16; ++jx) {
+    const int j = 16 * JB + jx;
+    double* cb = colbuf + (j & 1) * 128;
+    if (tx == jx) {
+#pragma unroll
+      for (int a = JB; a < 8; ++a) {
+        const int i = 16 * a + ty;
+        if (i >= j) cb[i] = r[a][JB];
+      }
+    }
+    __syncthreads();
+    const double pj = cb[j];
+    if (tx == jx) {
+      const double s = sqrt(pj);
+      const double inv = 1.0 / s;
+#pragma unroll
+      for (int a = JB; a < 8; ++a) {
+        const int i = 16 * a + ty;
+        if (i > j) Ls[i + j * LD] = r[a][JB] * inv;
+        if (i == j) {
+          dg[j] = s;
+          if (!(pj > 0.0)) atomicCAS(info, 0, blk * 128 + j + 1);
+        }
+      }
+    }
+    const double invp = 1.0 / pj;
+#pragma unroll
+    for (int a = JB; a < 8; ++a) {
+      const int i = 16 * a + ty;
+      if (i > j) {
+        const double li = cb[i] * invp;
+#pragma unroll
+        for (int b = JB; b <= a; ++b) {
+          const int k = 16 * b + tx;
+          if (k > j && k <= i) r[a][b] = fma(-li, cb[k], r[a][b]);
+        }
+      }
+    }
+  }
+}
+
+template <int JB>
+__device__ __forceinline__ void leaf_inv_block(double (&r)[8][8], double* Ls, double* rowbuf, const double* idg,
+                                               int tx, int ty) {
+  using namespace leaf;
+#pragma unroll 1
+  for (int jx = 0; jx < 16; ++jx) {
+    const int j = 16 * JB + jx;
+    double* rb = rowbuf + (j & 1) * 128;
+    if (ty == jx) {  // owners of row j (a == JB)
+      const double dj = idg[j];
+#pragma unroll
+      for (int b = 0; b <= JB; ++b) {
+        const int k = 16 * b + tx;
+        if (k <= j) {
+          const double x = r[JB][b] * dj;
+          rb[k] = x;
+          if (k < j) Ls[k + j * LD] = x;  // U(k,j) = X(j,k) into the (still unused) upper triangle
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = JB; a < 8; ++a) {
+      const int i = 16 * a + ty;
+      if (i > j) {
+        const double lij = Ls[i + j * LD];
+#pragma unroll
+        for (int b = 0; b <= JB; ++b) {
+          const int k = 16 * b + tx;
+          if (k <= j) r[a][b] = fma(-lij, rb[k], r[a][b]);
+        }
+      }
+    }
+  }
+}
+
+// A: matrix base, tile blk on its diagonal.  Writes L (lower of the tile), DX/DU tiles, dvec, info.
+__global__ void __launch_bounds__(256, 1) potrf_leaf_kernel(double* __restrict__ A, long ld, int blk,
+                                                            double* __restrict__ DX, double* __restrict__ DU,
+                                                            double* __restrict__ dvec, int* info) {
+  using namespace leaf;
+  extern __shared__ __align__(16) double sm[];
+  double* Ls = sm;
+  double* colbuf = Ls + 128 * LD;
+  double* rowbuf = colbuf + 256;
+  double* dg = rowbuf + 256;
+  double* idg = dg + 128;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double* At = A + (size_t)blk * 128 * (ld + 1);
+
+  for (int idx = threadIdx.x; idx < 128 * 128; idx += 256) {
+    const int i = idx & 127, k = idx >> 7;
+    Ls[i + k * LD] = At[i + (size_t)k * ld];
+  }
+  __syncthreads();
+  double r[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int i = 16 * a + ty, k = 16 * b + tx;
+      r[a][b] = (k <= i) ? Ls[i + k * LD] : 0.0;
+    }
+  __syncthreads();
+
+  leaf_chol_block<0>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<1>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<2>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<3>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<4>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<5>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<6>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<7>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  __syncthreads();
+  if (threadIdx.x < 128) idg[threadIdx.x] = 1.0 / dg[threadIdx.x];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) r[a][b] = (16 * a + ty == 16 * b + tx) ? 1.0 : 0.0;
+  __syncthreads();
+
+  leaf_inv_block<0>(r, Ls, rowbuf, idg, tx, ty);
+  leaf_inv_block<1>(r, Ls, rowbuf, idg, tx, ty);
+  leaf_inv_block<2>(r, Ls, rowbuf, idg, tx, ty);
+  leaf_inv_block<3>(r, Ls, rowbuf, idg, tx, ty);
+  leaf_inv_block<4>(r, Ls, rowbuf, idg, tx, ty);
+  leaf_inv_block<5>(r, Ls, rowbuf, idg, tx, ty);
+  leaf_inv_block<6>(r, Ls, rowbuf, idg, tx, ty);
+  leaf_inv_block<7>(r, Ls, rowbuf, idg, tx, ty);
+  __syncthreads();
+
+  double* DXt = DX + (size_t)blk * 128 * 128;
+  double* DUt = DU + (size_t)blk * 128 * 128;
+  for (int idx = threadIdx.x; idx < 128 * 128; idx += 256) {
+    const int i = idx & 127, k = idx >> 7;  // i fast: coalesced global writes
+    if (i > k) {
+      At[i + (size_t)k * ld] = Ls[i + k * LD];
+      DXt[idx] = Ls[k + i * LD];
+      DUt[idx] = 0.0;
+    } else if (i == k) {
+      At[i + (size_t)k * ld] = dg[i];
+      DXt[idx] = idg[i];
+      DUt[idx] = idg[i];
+    } else {
+      DXt[idx] = 0.0;
+      DUt[idx] = Ls[i + k * LD];
+    }
+  }
+  if (threadIdx.x < 128) dvec[blk * 128 + threadIdx.x] = dg[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Panel x 128-wide triangular block, in place:  P <- P * DX^T  (the leaf of the blocked TRSM
+// X L^T = P, with DX = L_kk^-1).  One CTA owns 64 full rows, so in-place is race free.
+// ---------------------------------------------------------------------------------------------
+namespace trsml {
+constexpr int ROWS = 64, LDA = ROWS + 4, LDB = 128 + 4;
+constexpr size_t SMEM_BYTES = (size_t)(128 * LDA + 128 * LDB) * 8 + 16;
+constexpr uint32_t TX_BYTES = (128 * ROWS + 128 * 128) * 8;
+}  // namespace trsml
+
+__global__ void __launch_bounds__(128, 1) trsm_leaf_kernel(double* __restrict__ P, long ld,
+                                                           const double* __restrict__ DXt) {
+  using namespace trsml;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double* As = reinterpret_cast<double*>(smraw);
+  double* Bs = As + 128 * LDA;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Bs + 128 * LDB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* Pr = P + (size_t)blockIdx.x * ROWS;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) mbar_arrive_expect_tx(bar, TX_BYTES);
+    __syncwarp();
+    for (int kk = lane; kk < 128; kk += 32) {
+      tma_bulk_g2s(As + kk * LDA, Pr + (size_t)kk * ld, ROWS * 8, bar);
+      tma_bulk_g2s(Bs + kk * LDB, DXt + (size_t)kk * 128, 128 * 8, bar);
+    }
+  }
+  mbar_wait(bar, 0);
+
+  const int g = lane >> 2, tq = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  const double* as = As + g;
+  const double* bs = Bs + warp * 32 + g;
+  const int ks_end = 8 * (warp + 1);  // DX lower triangular: column j only needs k <= j
+#pragma unroll 2
+  for (int ks = 0; ks < ks_end; ++ks) {
+    const int k = ks * 4 + tq;
+    double a[8], b[4];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) a[mt] = as[k * LDA + mt * 8];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = bs[k * LDB + nt * 8];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+  const int col0 = warp * 32 + 2 * tq;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double* cc = Pr + (size_t)(col0 + nt * 8 + e) * ld + g;
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) cc[mt * 8] = acc[mt][nt][e];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side drivers
+// ---------------------------------------------------------------------------------------------
+struct DenseWork {
+  double* A = nullptr;     // n_pad x n_pad
+  long ld = 0;
+  int nb = 0;              // n_pad / 128
+  double* DX = nullptr;    // nb tiles
+  double* DU = nullptr;    // nb tiles
+  double* dvec = nullptr;  // n_pad
+  int* info = nullptr;     // device int: 0, or 1-based index of the first non-positive pivot
+  double* Bf = nullptr;    // n_pad x n_pad: workspace, then the inverse
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
+  int panel_blocks = 4;    // look-ahead panel width in 128-blocks (512 columns)
+};
+
+inline int configure_dense_kernels() {
+  ACE_CUDA(cudaFuncSetAttribute(dgemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)gemm::SMEM_BYTES));
+  ACE_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)leaf::SMEM_BYTES));
+  ACE_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)trsml::SMEM_BYTES));
+  return 0;
+}
+
+inline double* blkptr(const DenseWork& w, int rb, int cb) { return w.A + (size_t)rb * TB + (size_t)cb * TB * w.ld; }
+
+inline int gemm_plain(const DenseWork& w, const double* A, const double* B, double* C, int M, int N, int K,
+                      double alpha, double beta, int lower_only, cudaStream_t st) {
+  GemmNT p{};
+  p.A = A; p.lda = w.ld; p.B = B; p.ldb = w.ld; p.C = C; p.ldc = w.ld;
+  p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only;
+  return launch_gemm_nt(p, st);
+}
+
+// rows [r0,r1) x tri [a,c):  A[r0:r1, a:c] <- A[r0:r1, a:c] * L[a:c,a:c]^-T   (recursive TRSM)
+inline int trsm_rec(const DenseWork& w, int r0, int r1, int a, int c, cudaStream_t st) {
+  if (r1 <= r0) return 0;
+  if (c - a == 1) {
+    trsm_leaf_kernel<<<(unsigned)((r1 - r0) * TB / trsml::ROWS), 128, trsml::SMEM_BYTES, st>>>(
+        blkptr(w, r0, a), w.ld, w.DX + (size_t)a * TB * TB);
+    ACE_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const int m = a + (c - a + 1) / 2;
+  ACE_TRY(trsm_rec(w, r0, r1, a, m, st));
+  ACE_TRY(gemm_plain(w, blkptr(w, r0, a), blkptr(w, m, a), blkptr(w, r0, m), (r1 - r0) * TB, (c - m) * TB,
+                     (m - a) * TB, -1.0, 1.0, 0, st));
+  return trsm_rec(w, r0, r1, m, c, st);
+}
+
+// Cholesky of the diagonal block range [a,b) (small, runs on one stream)
+inline int potrf_rec(const DenseWork& w, int a, int b, cudaStream_t st) {
+  if (b - a == 1) {
+    potrf_leaf_kernel<<<1, 256, leaf::SMEM_BYTES, st>>>(w.A, w.ld, a, w.DX, w.DU, w.dvec, w.info);
+    ACE_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const int c = a + (b - a + 1) / 2;
+  ACE_TRY(potrf_rec(w, a, c, st));
+  ACE_TRY(trsm_rec(w, c, b, a, c, st));
+  ACE_TRY(gemm_plain(w, blkptr(w, c, a), blkptr(w, c, a), blkptr(w, c, c), (b - c) * TB, (b - c) * TB,
+                     (c - a) * TB, -1.0, 1.0, 1, st));
+  return potrf_rec(w, c, b, st);
+}
+
+// Phase 1: right-looking blocked Cholesky with one-panel look-ahead on two streams.
+//   panel(J)  : factor the diagonal block + TRSM of the rows below it        (side stream)
+//   upd_a(J)  : trailing update restricted to the next panel's block column  (main stream)
+//   upd_b(J)  : the rest of the trailing update                              (main stream)
+// panel(J+1) only waits for upd_a(J), so it overlaps upd_b(J).
+inline int potrf_blocked(const DenseWork& w) {
+  const int nb = w.nb, pb = w.panel_blocks;
+  ACE_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int), w.main));
+  // fork: side stream joins after everything already queued on main
+  ACE_CUDA(cudaEventRecord(w.ev_upd[1], w.main));
+  ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_upd[1], 0));
+  int J = 0;
+  for (int j0 = 0; j0 < nb; j0 += pb, ++J) {
+    const int j1 = min(j0 + pb, nb), j2 = min(j1 + pb, nb);
+    // ---- panel(J) on the side stream
+    ACE_TRY(potrf_rec(w, j0, j1, w.side));
+    ACE_TRY(trsm_rec(w, j1, nb, j0, j1, w.side));
+    ACE_CUDA(cudaEventRecord(w.ev_panel[J & 1], w.side));
+    if (j1 >= nb) break;
+    // ---- trailing update on the main stream
+    ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_panel[J & 1], 0));
+    const int K = (j1 - j0) * TB;
+    // upd_a: rows [j1,nb) x cols [j1,j2)
+    ACE_TRY(gemm_plain(w, blkptr(w, j1, j0), blkptr(w, j1, j0), blkptr(w, j1, j1), (nb - j1) * TB,
+                       (j2 - j1) * TB, K, -1.0, 1.0, 0, w.main));
+    ACE_CUDA(cudaEventRecord(w.ev_upd[J & 1], w.main));
+    ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_upd[J & 1], 0));
+    // upd_b: square block [j2,nb) lower tiles
+    if (j2 < nb)
+      ACE_TRY(gemm_plain(w, blkptr(w, j2, j0), blkptr(w, j2, j0), blkptr(w, j2, j2), (nb - j2) * TB,
+                         (nb - j2) * TB, K, -1.0, 1.0, 1, w.main));
+  }
+  // join
+  ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_panel[J & 1], 0));
+  return 0;
+}
+
+// Phase 2: U = L^-T into upper(A) (and X = L^-1 into lower(A)) by bottom-up pairwise merging.
+// For a node with children [a,c) and [c,b):   X21 = -X22 * L21 * X11, done as two NT GEMMs
+//   Wt  = U11 * L21^T              (A operand upper triangular, diagonal tiles from DU)
+//   X21 = -X22 * Wt^T, U12 = X21^T (A operand lower triangular, diagonal tiles from DX; dual store)
+// Wt lives in Bf.  All nodes of one level are independent; equal-shaped ones go in one batched launch.
+inline int& dbg_trtri_max_h() {
+  static int v = 1 << 30;
+  return v;
+}
+
+inline int trtri_merge(const DenseWork& w) {
+  const int nb = w.nb;
+  cudaStream_t st = w.main;
+  for (int h = 1; h < nb && h <= dbg_trtri_max_h(); h *= 2) {
+    const int nodes = (nb + 2 * h - 1) / (2 * h);
+    const int s1 = h * TB;
+    // regular nodes (full right child) q = 0 .. nreg-1 in one strided-batched launch, ragged last node alone
+    int nreg = 0;
+    while (nreg < nodes && (nreg * 2 * h + 2 * h) <= nb) ++nreg;
+    for (int pass = 0; pass < 2; ++pass) {
+      int q0, cnt, s2;
+      if (pass == 0) {
+        q0 = 0; cnt = nreg; s2 = s1;
+      } else {
+        q0 = nreg; cnt = nodes - nreg;  // 0 or 1
+        if (cnt == 0) break;
+        const int c = q0 * 2 * h + h;
+        if (c >= nb) break;  // lone left child, nothing to merge
+        s2 = (nb - c) * TB;
+      }
+      if (cnt == 0) continue;
+      const int a = q0 * 2 * h, c = a + h;
+      const long node_stride = (long)2 * h * TB * (w.ld + 1);
+      double* Wt = w.Bf + (size_t)q0 * s1 * s1;
+      GemmNT p{};
+      p.A = blkptr(w, a, a); p.lda = w.ld; p.a_tri = 1; p.Adiag = w.DU + (size_t)a * TB * TB;
+      p.B = blkptr(w, c, a); p.ldb = w.ld;
+      p.C = Wt; p.ldc = s1;
+      p.M = s1; p.N = s2; p.K = s1; p.alpha = 1.0; p.beta = 0.0;
+      p.batch = cnt; p.sA = node_stride; p.sB = node_stride; p.sC = (long)s1 * s1;
+      p.sAdiag = (long)2 * h * TB * TB;
+      ACE_TRY(launch_gemm_nt(p, st));
+      GemmNT r{};
+      r.A = blkptr(w, c, c); r.lda = w.ld; r.a_tri = 2; r.Adiag = w.DX + (size_t)c * TB * TB;
+      r.B = Wt; r.ldb = s1;
+      r.C = blkptr(w, c, a); r.ldc = w.ld;
+      r.Ct = blkptr(w, a, c); r.ldct = w.ld;
+      r.M = s2; r.N = s1; r.K = s2; r.alpha = -1.0; r.beta = 0.0;
+      r.batch = cnt; r.sA = node_stride; r.sB = (long)s1 * s1; r.sC = node_stride; r.sCt = node_stride;
+      r.sAdiag = (long)2 * h * TB * TB;
+      ACE_TRY(launch_gemm_nt(r, st));
+    }
+  }
+  return 0;
+}
+
+// Phase 3: inverse = U * U^T into Bf (both triangles), one launch.
+inline int uut_inverse(const DenseWork& w) {
+  GemmNT p{};
+  p.A = w.A; p.lda = w.ld; p.a_tri = 1; p.Adiag = w.DU;
+  p.B = w.A; p.ldb = w.ld; p.Bdiag = w.DU;
+  p.C = w.Bf; p.ldc = w.ld; p.Ct = w.Bf; p.ldct = w.ld;
+  p.M = p.N = p.K = w.nb * TB;
+  p.alpha = 1.0; p.beta = 0.0; p.lower_only = 1;
+  return launch_gemm_nt(p, w.main);
+}
+
+inline int spd_inverse(const DenseWork& w) {
+  ACE_TRY(potrf_blocked(w));
+  ACE_TRY(trtri_merge(w));
+  return uut_inverse(w);
+}
+
+}  // namespace ace

@@ -1,0 +1,201 @@
+/* ace_b200.h -- C ABI of the B200-native hot path of AdditiveCausalExpansion (R package `ace` 0.4.1).
+ *
+ * This is the drop-in boundary: a thin Rcpp shim keeps the 19 `.Call` routines of the reference
+ * (src/RcppExports.cpp:301-327) and marshals each to the entry point below that carries the same
+ * name with an `ace_` prefix.  File:line citations are relative to the reference checkout.
+ *
+ * Conventions (all entry points):
+ *   - every array is FP64, COLUMN-MAJOR, densely packed (leading dimension = number of rows), in HOST
+ *     memory owned by the caller; outputs are caller-allocated; nothing is retained after return
+ *     except through an `ace_fit` handle;
+ *   - X is n x p, Z is n x Bz (the basis matrix, `Basis$B`), B = Bz + 1 additive terms,
+ *     parameters has P = 2 + B + B*p entries laid out as in R/parameters.R:15-20
+ *     (sigma, mu, lambda[B], L[B*p] with L(d,b) at 2 + B + b + B*d);
+ *   - cubes are n1 x n2 x B with element (r,c,s) at r + n1*c + n1*n2*s;
+ *   - return value: 0 = ok; > 0 = numerical failure (1-based index of the first non-positive
+ *     Cholesky pivot, or ACE_ERR_NOT_FINITE); < 0 = usage / CUDA error.  ace_last_error() gives text.
+ *   - calls are blocking and must not be issued concurrently on the same handle; different handles
+ *     (also on different devices) may be driven from different host threads.
+ *   - there is NO CPU fallback: without a CUDA device the compute entry points fail with
+ *     ACE_ERR_NO_DEVICE.  The four O(n) preprocessing routines at the end are host code, as in the
+ *     reference.
+ */
+#ifndef ACE_B200_H
+#define ACE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACE_OK 0
+#define ACE_ERR_NOT_FINITE 1073741824 /* gradients not finite (R/optimizer_classes.R:26-29,58-61,87-89) */
+#define ACE_ERR_USAGE (-1)
+#define ACE_ERR_NO_DEVICE (-3)
+#define ACE_ERR_UNSUPPORTED (-4)
+
+#define ACE_KERNEL_SE 0
+#define ACE_KERNEL_MATERN32 1
+#define ACE_OPT_NADAM 0
+#define ACE_OPT_ADAM 1
+#define ACE_OPT_NESTEROV 2 /* "GD" (momentum 0) and "NAG" */
+
+const char* ace_last_error(void);
+const char* ace_version(void);
+int ace_device_count(void);      /* number of CUDA devices visible, 0 if none */
+int ace_set_device(int device);  /* device used by the per-function entry points of this thread */
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-function entry points (one per reference export; host in, host out)
+ * ------------------------------------------------------------------------------------------- */
+
+/* kernmat_SE_cpp (src/kernel_SE_cpp.cpp:9-64) / kernmat_Matern32_cpp (src/kernel_Matern_cpp.cpp:52-93).
+ * full: n1 x n2.  elements: n1 x n2 x B or NULL (skip the cube). */
+int ace_kernmat_SE_cpp(const double* X1, const double* X2, const double* Z1, const double* Z2, int n1, int n2,
+                       int p, int Bz, const double* parameters, double* full, double* elements);
+int ace_kernmat_Matern32_cpp(const double* X1, const double* X2, const double* Z1, const double* Z2, int n1,
+                             int n2, int p, int Bz, const double* parameters, double* full, double* elements);
+
+/* kernmat_SE_symmetric_cpp (src/kernel_SE_cpp.cpp:67-134) / kernmat_Matern32_symmetric_cpp
+ * (src/kernel_Matern_cpp.cpp:190-240).  full: n x n, exactly symmetric.  elements: n x n x B or NULL. */
+int ace_kernmat_SE_symmetric_cpp(const double* X, const double* Z, int n, int p, int Bz,
+                                 const double* parameters, double* full, double* elements);
+int ace_kernmat_Matern32_symmetric_cpp(const double* X, const double* Z, int n, int p, int Bz,
+                                       const double* parameters, double* full, double* elements);
+
+/* invkernel_cpp (src/kernel_SE_cpp.cpp:137-157): inv = (pdmat + e^sigma I)^-1.
+ * The reference returns the eigenvalues only to take sum(log(.)) of them
+ * (src/include/ace_kernel_utils.hpp:34); the `eigenval` slot here receives diag(L)^2 of the
+ * Cholesky factor, whose sum of logs is the same log-determinant (not sorted eigenvalues). */
+int ace_invkernel_cpp(const double* pdmat, int n, double sigma, double* eigenval, double* inv);
+
+/* grad_SE_cpp (src/kernel_SE_cpp.cpp:192-243) / grad_Matern_cpp (src/kernel_Matern_cpp.cpp:420-467).
+ * Kfull and K (cube) are accepted for signature compatibility and may be NULL: the additive terms
+ * are recomputed on the device from (X, Z, parameters), which is what the R6 callers pass anyway
+ * (R/kernel_SE_R6.R:47-50).  Z must be the basis matrix the kernel was built with.
+ * stats[2] = (RMSE, log-evidence) is written in place like the reference's `arma::vec& stats`. */
+int ace_grad_SE_cpp(const double* y, const double* X, const double* Z, const double* Kfull, const double* K,
+                    const double* invKmatn, const double* eigenval, const double* parameters, double* stats,
+                    unsigned int B, double std_y, int n, int p, double* gradients);
+int ace_grad_Matern_cpp(const double* y, const double* X, const double* Z, const double* Kfull, const double* K,
+                        const double* invKmatn, const double* eigenval, const double* parameters, double* stats,
+                        unsigned int B, double std_y, int n, int p, double* gradients);
+
+/* stats_cpp (src/stats_cpp.cpp:9-32): out[2] = (RMSE, log-evidence). */
+int ace_stats_cpp(const double* y, const double* Kmat, const double* invKmatn, const double* eigenval, double mu,
+                  double std_y, int n, double* out);
+
+/* mu_solution_cpp (src/utilities_cpp.cpp:6-10). */
+int ace_mu_solution_cpp(const double* y, const double* invKmat, int n, double* mu);
+
+/* pred_cpp (src/pred_cpp.cpp:8-34).  K_xX: nx x nX, K_xx: nx x nx (only its diagonal is used).
+ * map: nx, ci: nx x 2, var: nx. */
+int ace_pred_cpp(const double* y_X, double sigma, double mu, const double* invK_XX, const double* K_xX,
+                 const double* K_xx, double mean_y, double std_y, int nx, int nX, double* map, double* ci,
+                 double* var);
+
+/* pred_marginal_cpp (src/pred_cpp.cpp:37-126).  K_xX: nx x nX x B, K_xx: nx x nx x B.
+ * avg (12 doubles, only written when calculate_ate): {map, ci_lo, ci_hi, var} for ate, att, atu. */
+int ace_pred_marginal_cpp(const double* y_X, const double* Z_x, double sigma, double mu, const double* invK_XX,
+                          const double* K_xX, const double* K_xx, double mean_y, double std_y, double std_Z,
+                          int calculate_ate, int nx, int nX, int B, double* map, double* ci, double* var,
+                          double* avg);
+
+/* norm_clip_cpp (src/utilities_cpp.cpp:121-129) and the optimisers (src/optimizer_cpp.cpp:8-63):
+ * O(P) host arithmetic, in place on the caller's vectors exactly like the reference's `arma::vec&`.
+ * The optimisers return 1 if every gradient entry was finite, 0 otherwise (the reference's bool). */
+void ace_norm_clip_cpp(int flag, double* grads, int P, double max_length);
+int ace_Nesterov_cpp(double learn_rate, double momentum, double* nu, const double* grad, double* para, int P);
+int ace_Nadam_cpp(double iter, double learn_rate, double beta1, double beta2, double eps, double* m, double* v,
+                  const double* grad, double* para, int P);
+int ace_Adam_cpp(double iter, double learn_rate, double beta1, double beta2, double eps, double* m, double* v,
+                 const double* grad, double* para, int P);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused, device-resident fit handle: the body of Kernel$para_update / get_train_stats / predict
+ * (R/kernel_SE_R6.R:40-97, R/kernel_Matern32_R6.R:39-98) + Optim$update (R/optimizer_classes.R).
+ * K, K^-1 and the optimiser state never leave the device; one iteration moves 4 doubles D2H.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ace_fit ace_fit;
+
+typedef struct ace_fit_config {
+  int kernel;        /* ACE_KERNEL_* */
+  int optimizer;     /* ACE_OPT_*    */
+  double learning_rate, beta1, beta2, momentum; /* R/main_ace.R:139-142 */
+  int norm_clip;     /* R/main_ace.R:143 (TRUE for Adam/Nadam) */
+  double clip_at;    /* accepted; the reference rescales to unit norm whatever its value */
+  double std_y;      /* moments[1,2], scales the RMSE */
+  int device;        /* CUDA device ordinal */
+  int use_graph;     /* 1: capture the iteration into a CUDA graph and replay it */
+} ace_fit_config;
+
+void ace_fit_default_config(ace_fit_config* cfg);
+
+int ace_fit_create(ace_fit** out, const double* y, const double* X, const double* Z, int n, int p, int Bz,
+                   const double* parameters, const ace_fit_config* cfg);
+int ace_fit_destroy(ace_fit* fit);
+
+/* One Kernel$para_update(iter, ...): build K, factor, invert, (iter == 1: closed-form mu), gradients,
+ * clip, optimiser step, mu refresh with the pre-update inverse.  stats[2] = (RMSE, log-evidence) of the
+ * parameters the iteration STARTED from; gnorm = L2 norm of the (clipped) gradient (both may be NULL).
+ * Returns ACE_ERR_NOT_FINITE where the reference's optimiser classes call stop(). */
+int ace_fit_para_update(ace_fit* fit, int iter, double* stats, double* gnorm);
+
+/* The loop of ace.train (R/main_ace.R:213-227): iterations iter_start .. at most iter_start+max_iter-1,
+ * stopping when |ev_t - ev_{t-1}| < tol and iter > 3 (prev_evidence: ev of iteration iter_start-1, 0 at the
+ * start like the reference's zero column).  stats_out: 2 x max_iter.  iters_done: iterations executed. */
+int ace_fit_run(ace_fit* fit, int iter_start, int max_iter, double tol, double prev_evidence, double* stats_out,
+                int* iters_done);
+
+/* Kernel$get_train_stats (R/kernel_SE_R6.R:63-74): rebuilds K and a LOCAL inverse with the current
+ * parameters; the stored inverse (invKmatn) is left untouched, as in the reference. */
+int ace_fit_get_train_stats(ace_fit* fit, double* stats);
+
+int ace_fit_get_parameters(ace_fit* fit, double* parameters);
+int ace_fit_set_parameters(ace_fit* fit, const double* parameters);
+int ace_fit_get_gradients(ace_fit* fit, double* gradients);      /* last (clipped) gradient vector */
+int ace_fit_get_optimizer_state(ace_fit* fit, double* m, double* v);
+int ace_fit_get_invKmatn(ace_fit* fit, double* inv);             /* n x n, the R6 field invKmatn */
+int ace_fit_get_alpha(ace_fit* fit, double* alpha);              /* n, K^-1 (y - mu) of the last iteration */
+int ace_fit_dims(ace_fit* fit, int* n, int* p, int* B, int* P);
+/* device time of the phases of the last para_update in ms: build, potrf, trtri, uut, gemv+grad, total */
+int ace_fit_last_timing(ace_fit* fit, double* ms6);
+
+/* Kernel$predict (R/kernel_SE_R6.R:75-83): posterior mean / CI / variance at nx new points with the
+ * stored invKmatn and the CURRENT parameters.  X2: nx x p, Z2: nx x Bz. */
+int ace_fit_predict(ace_fit* fit, const double* X2, const double* Z2, int nx, double mean_y, double std_y,
+                    double* map, double* ci, double* var);
+/* Kernel$predict_marginal (R/kernel_SE_R6.R:84-97).  Z2: nx x Bz basis at the new points (its first
+ * column is the Z_x of pred_marginal_cpp), dZ2: nx x Bz basis derivative. */
+int ace_fit_predict_marginal(ace_fit* fit, const double* X2, const double* Z2, const double* dZ2, int nx,
+                             double mean_y, double std_y, double std_Z, int calculate_ate, double* map,
+                             double* ci, double* var, double* avg);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense building blocks, exported for tests and benchmarks (host in / host out)
+ * ------------------------------------------------------------------------------------------- */
+/* C = beta*C + alpha*A*B^T with the DMMA kernel; M, N, K multiples of 128. */
+int ace_dbg_gemm_nt(const double* A, const double* B, double* C, int M, int N, int K, double alpha, double beta,
+                    int lower_only);
+/* Cholesky + inverse of an SPD matrix (any n): L (lower, n x n, may be NULL), inv (n x n, may be NULL),
+ * diagL (n, may be NULL).  ms3 (may be NULL): device ms of potrf, trtri, uut. */
+int ace_dbg_spd_inverse(const double* A, int n, double* L, double* inv, double* diagL, double* ms3);
+/* potrf-only timing on a synthetic SPD matrix generated on the device: returns ms of potrf / trtri / uut
+ * averaged over `reps` runs after one warm-up; no host transfer of the matrix. */
+int ace_bench_dense(int n, int reps, double* ms3);
+
+/* ---------------------------------------------------------------------------------------------
+ * O(n) preprocessing, host code as in the reference (same DLL, not on the hot path)
+ * ------------------------------------------------------------------------------------------- */
+/* ncs_basis / ncs_basis_deriv (src/ncs_basis_cpp.cpp:61-99): returns the number of columns (= number of
+ * unique knots); design (n x ncol) may be NULL to query the size. */
+int ace_ncs_basis(const double* x, int n, const double* knots, int nknots, double* design);
+int ace_ncs_basis_deriv(const double* x, int n, const double* knots, int nknots, double* design);
+/* normalize_train / normalize_test (src/utilities_cpp.cpp:13-118): in place on y, X (n x px), Z (n x pz);
+ * moments: (1 + px + pz) x 3. */
+int ace_normalize_train(double* y, double* X, double* Z, int n, int px, int pz, double* moments);
+int ace_normalize_test(double* X, double* Z, int n, int px, int pz, const double* moments);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACE_B200_H */
