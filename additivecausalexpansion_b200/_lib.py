@@ -78,6 +78,10 @@ SIGNATURES = {
     "ace_fit_para_update": (_i, [_vp, _i, _p, _p]),
     "ace_fit_run": (_i, [_vp, _i, _i, _d, _d, _p, _ip]),
     "ace_fit_get_train_stats": (_i, [_vp, _p]),
+    "ace_fit_upload_data": (_i, [_vp, _p, _p, _p]),
+    "ace_fit_kernel_launches": (_i, [_vp, _ip]),
+    "ace_fit_timer_start": (_i, [_vp]),
+    "ace_fit_timer_stop": (_i, [_vp, _p]),
     "ace_fit_get_parameters": (_i, [_vp, _p]),
     "ace_fit_set_parameters": (_i, [_vp, _p]),
     "ace_fit_get_gradients": (_i, [_vp, _p]),
@@ -91,6 +95,8 @@ SIGNATURES = {
     "ace_dbg_gemm_nt": (_i, [_p, _p, _p, _i, _i, _i, _d, _d, _i]),
     "ace_dbg_spd_inverse": (_i, [_p, _i, _p, _p, _p, _p]),
     "ace_bench_dense": (_i, [_i, _i, _p]),
+    "ace_dbg_set_trtri_max_h": (_i, [_i]),
+    "ace_dbg_trtri_raw": (_i, [_p, _i, _p, _p, _p, _p]),
     "ace_ncs_basis": (_i, [_p, _i, _p, _i, _p]),
     "ace_ncs_basis_deriv": (_i, [_p, _i, _p, _i, _p]),
     "ace_normalize_train": (_i, [_p, _p, _p, _i, _i, _i, _p]),

@@ -14,6 +14,7 @@
 
 #include "chol.cuh"
 #include "gp_kernels.cuh"
+#include "pair_kernels.cuh"
 #include "pred_kernels.cuh"
 
 namespace ace {
@@ -122,27 +123,13 @@ __global__ void synth_spd_kernel(double* A, long ld, int n) {
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
-template <int BMAX>
-static int launch_kernmat_b(const KernArgs& a, int kind, size_t smem, unsigned grid, cudaStream_t st) {
-  if (kind == 0) {
-    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<BMAX, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernmat_kernel<BMAX, 0><<<grid, 256, smem, st>>>(a);
-  } else {
-    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<BMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernmat_kernel<BMAX, 1><<<grid, 256, smem, st>>>(a);
-  }
-  ACE_CUDA(cudaGetLastError());
-  return 0;
-}
-
 static int launch_kernmat(const KernArgs& a, int kind, cudaStream_t st) {
   const int B = a.B;
   if (B < 1 || B > BMAXT || a.p < 1 || a.p > PMAX) {
     set_error("kernel build supports 1 <= p <= 64 and B = Bz+1 <= 32");
     return ACE_ERR_UNSUPPORTED;
   }
-  const int bmax = B <= 2 ? 2 : B <= 4 ? 4 : B <= 8 ? 8 : B <= 12 ? 12 : B <= 16 ? 16 : 32;
-  const size_t smem = kb::smem_bytes(a.p, B - 1, bmax, a.sym != 0);
+  const size_t smem = kb::smem_bytes(a.p, B - 1, a.sym != 0);
   if (smem > 227 * 1024) {
     set_error("kernel build: p and Bz too large for one shared-memory tile");
     return ACE_ERR_UNSUPPORTED;
@@ -154,14 +141,15 @@ static int launch_kernmat(const KernArgs& a, int kind, cudaStream_t st) {
   } else {
     grid = (unsigned)((a.n1_pad / kb::T) * (a.n2_pad / kb::T));
   }
-  switch (bmax) {
-    case 2: return launch_kernmat_b<2>(a, kind, smem, grid, st);
-    case 4: return launch_kernmat_b<4>(a, kind, smem, grid, st);
-    case 8: return launch_kernmat_b<8>(a, kind, smem, grid, st);
-    case 12: return launch_kernmat_b<12>(a, kind, smem, grid, st);
-    case 16: return launch_kernmat_b<16>(a, kind, smem, grid, st);
-    default: return launch_kernmat_b<32>(a, kind, smem, grid, st);
+  if (kind == 0) {
+    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernmat_kernel<0><<<grid, 256, smem, st>>>(a);
+  } else {
+    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernmat_kernel<1><<<grid, 256, smem, st>>>(a);
   }
+  ACE_CUDA(cudaGetLastError());
+  return 0;
 }
 
 struct GradPlan {
@@ -400,11 +388,15 @@ using namespace ace;
 struct ace_fit {
   Core c;
   ace_fit_config cfg;
+  cudaEvent_t sw0 = nullptr, sw1 = nullptr;  // stopwatch
+  int launches = -1;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   double iter_dev = 0.0;  // host shadow of sc[SC_ITER]
   double ms[6] = {0, 0, 0, 0, 0, 0};
   ~ace_fit() {
+    if (sw0) cudaEventDestroy(sw0);
+    if (sw1) cudaEventDestroy(sw1);
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
   }
@@ -601,6 +593,74 @@ int ace_fit_get_train_stats(ace_fit* f, double* stats) {
   stats[0] = c.h_sc[SC_RMSE];
   stats[1] = c.h_sc[SC_EVID];
   if (c.h_info() > 0) return c.h_info();
+  return 0;
+}
+
+int ace_fit_upload_data(ace_fit* f, const double* y, const double* X, const double* Z) {
+  if (!f) return usage("null handle");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  return f->c.upload_data(y, X, Z);  // stream ordered before the next para_update
+}
+
+static int count_kernel_nodes(cudaGraph_t g, int* out) {
+  size_t nn = 0;
+  ACE_CUDA(cudaGraphGetNodes(g, nullptr, &nn));
+  std::vector<cudaGraphNode_t> nodes(nn);
+  if (nn) ACE_CUDA(cudaGraphGetNodes(g, nodes.data(), &nn));
+  int k = 0;
+  for (size_t i = 0; i < nn; ++i) {
+    cudaGraphNodeType t;
+    ACE_CUDA(cudaGraphNodeGetType(nodes[i], &t));
+    if (t == cudaGraphNodeTypeKernel) ++k;
+  }
+  *out = k;
+  return 0;
+}
+
+int ace_fit_kernel_launches(ace_fit* f, int* launches) {
+  if (!f || !launches) return usage("null argument");
+  Core& c = f->c;
+  ACE_CUDA(cudaSetDevice(c.device));
+  if (f->launches < 0) {
+    if (f->graph) {
+      ACE_TRY(count_kernel_nodes(f->graph, &f->launches));
+    } else {  // capture once just to count; nothing is executed
+      ACE_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeThreadLocal));
+      int s = enqueue_iteration(f, false);
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(c.st, &g);
+      if (s != 0 || e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        return s != 0 ? s : -(int)e - 1000;
+      }
+      s = count_kernel_nodes(g, &f->launches);
+      cudaGraphDestroy(g);
+      ACE_TRY(s);
+    }
+  }
+  *launches = f->launches;
+  return 0;
+}
+
+int ace_fit_timer_start(ace_fit* f) {
+  if (!f) return usage("null handle");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  if (!f->sw0) {
+    ACE_CUDA(cudaEventCreate(&f->sw0));
+    ACE_CUDA(cudaEventCreate(&f->sw1));
+  }
+  ACE_CUDA(cudaEventRecord(f->sw0, f->c.st));
+  return 0;
+}
+
+int ace_fit_timer_stop(ace_fit* f, double* ms) {
+  if (!f || !ms || !f->sw0) return usage("timer not started");
+  ACE_CUDA(cudaSetDevice(f->c.device));
+  ACE_CUDA(cudaEventRecord(f->sw1, f->c.st));
+  ACE_CUDA(cudaEventSynchronize(f->sw1));
+  float t = 0;
+  ACE_CUDA(cudaEventElapsedTime(&t, f->sw0, f->sw1));
+  *ms = t;
   return 0;
 }
 

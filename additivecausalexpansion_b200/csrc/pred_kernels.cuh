@@ -2,7 +2,7 @@
 // The O(nx * n^2) product K_xX * K^-1 itself runs in dgemm_nt_kernel; these are the O(nx * n) rows
 // and the O(nx^2) averages of pred_marginal_cpp.
 #pragma once
-#include "gp_kernels.cuh"
+#include "pair_kernels.cuh"
 
 namespace ace {
 
@@ -82,7 +82,7 @@ __global__ void kdiag_kernel(const double* __restrict__ Z, const double* __restr
       lz = LZ[i + (size_t)(b - 1) * ld];
     }
     const double lam = tab[TAB_LAM + b];
-    s += (kind == 0) ? term_value<0>(b, lam, 0.0, z, z, lz, lz) : term_value<1>(b, lam, 0.0, z, z, lz, lz);
+    s += (kind == 0) ? term_value<0>(b, lam, 0.0, z, z, lz, lz) : term_value<1>(b, lam, 0.0, z, z, lz, lz);  // D = r = 0
   }
   out[i] = s;
 }

@@ -89,6 +89,28 @@ class AceFit:
                                 _p(stats), C.byref(done)), "ace_fit_run")
         return done.value, stats[:, :done.value].copy()
 
+    def upload_data(self, y=None, X=None, Z=None):
+        """Host -> device copy of the training data (what the per-call y, X, Z arguments of
+        Kernel$para_update amount to)."""
+        y = None if y is None else _f(y).ravel()
+        X = None if X is None else _f(X, True)
+        Z = None if Z is None else _f(Z, True)
+        check(lib().ace_fit_upload_data(self._h, _p(y), _p(X), _p(Z)), "ace_fit_upload_data")
+
+    @property
+    def kernel_launches(self):
+        k = C.c_int(0)
+        check(lib().ace_fit_kernel_launches(self._h, C.byref(k)), "ace_fit_kernel_launches")
+        return k.value
+
+    def timer_start(self):
+        check(lib().ace_fit_timer_start(self._h), "ace_fit_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double(0.0)
+        check(lib().ace_fit_timer_stop(self._h, C.cast(C.byref(ms), c_double_p)), "ace_fit_timer_stop")
+        return ms.value
+
     def get_train_stats(self):
         st = np.zeros(2)
         check(lib().ace_fit_get_train_stats(self._h, _p(st)), "ace_fit_get_train_stats")

@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- Nadam iterations/s of the ACE empirical-Bayes GP step at n = 16384 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3]
+
+A "step" is one Kernel$para_update (kernel build + Cholesky + inverse + evidence + all P gradients +
+clip + Nadam + mu refresh) on the configuration the metric is quoted on (C3: n=16384, p=20, Matern-3/2,
+cubic B-spline with 8 interior knots -> B=12, P=254).  Under torchrun (N > 1) every rank runs an
+independent restart of the same configuration on its own GPU (north star: "independent restarts ... one
+per GPU"), so scaling is weak and value = N*K / max-over-ranks time.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "nadam_iters_per_sec"
+UNIT = "iter/s"
+
+
+def workload_name(prob, cfg):
+    return (f"{cfg}: n={prob.n}, p={prob.p}, {prob.kernel} kernel, B={prob.B} additive terms "
+            f"(P={2 + prob.B + prob.B * prob.p} parameters), one Kernel$para_update per step, Nadam lr=0.01 clip on")
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(cfg, n_sample, steps, nthreads):
+    """Times the oracle's Kernel$para_update (literal restatement of the reference, dsyevd inverse) on the
+    box's host cores at a reduced n and scales each stage to the full n of the workload: build and
+    gradient loop ~ n^2, eigendecomposition + V V' ~ n^3 (favourable to the CPU: cache effects that make
+    the n^2 stages grow faster are ignored).  Returns (seconds per iteration at full n, detail)."""
+    import oracle
+    from additivecausalexpansion_b200 import synth
+
+    oracle.lib(nthreads)
+    full = synth.CONFIGS[cfg]["n"]
+    prob = synth.make_problem(cfg, n=n_sample)
+    of = oracle.OracleFit(prob.y, prob.X, prob.Z, prob.parameters, kernel=prob.kernel, std_y=prob.std_y)
+    per_step, stages = [], []
+    for it in range(1, steps + 1):
+        t0 = time.perf_counter()
+        of.para_update(it)
+        per_step.append(time.perf_counter() - t0)
+        stages.append(of.tsec.copy())
+    st = np.median(np.array(stages), axis=0)  # build, inverse, gradient, rest
+    r = full / n_sample
+    t_full = st[0] * r ** 2 + st[1] * r ** 3 + st[2] * r ** 2 + st[3] * r ** 2
+    detail = {"n_sample": n_sample, "sec_per_iter_at_sample": float(np.median(per_step)),
+              "stage_sec_at_sample": {"build": float(st[0]), "dsyevd_inverse": float(st[1]),
+                                      "gradient_loop": float(st[2]), "rest": float(st[3])},
+              "sec_per_iter_scaled_to_full_n": float(t_full), "threads": oracle.threads()}
+    return t_full, detail, per_step
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    from additivecausalexpansion_b200 import synth
+
+    prob_small = synth.make_problem(args.config, n=args.cpu_n)
+    t_full, detail, per_step = cpu_sample(args.config, args.cpu_n, max(1, min(args.steps, 3)), cores)
+    value = 1.0 / t_full
+    full_n = synth.CONFIGS[args.config]["n"]
+    sample = (f"oracle port of the reference (literal loops, LAPACK dsyevd inverse) timed for "
+              f"{len(per_step)} para_update(s) at n={args.cpu_n} (same p, B, kernel), stages scaled to n={full_n}: "
+              f"build, gradient loop x(n/n_s)^2, dsyevd+VV' x(n/n_s)^3")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(_FullShape(prob_small, full_n), args.config)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": detail["threads"], "kind": "port",
+                             "sample": sample, "detail": detail},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+class _FullShape:
+    def __init__(self, prob, n):
+        self.n, self.p, self.B, self.kernel = n, prob.p, prob.B, prob.kernel
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    from additivecausalexpansion_b200 import synth
+    from additivecausalexpansion_b200.kernel import (KernelClass_Matern32_R6, KernelClass_SE_R6, set_optimizer)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # independent restart per rank: same configuration, rank-specific synthetic draw
+    prob = synth.make_problem(args.config, n=args.n, seed_offset=rank)
+    cls = KernelClass_Matern32_R6 if prob.kernel == "Matern32" else KernelClass_SE_R6
+
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a.T)).pin_memory().numpy().T  # Fortran view, pinned
+
+    y, X, Z = pinned(prob.y.reshape(-1, 1))[:, 0], pinned(prob.X), pinned(prob.Z)
+    K = cls(prob.p, prob.B, prob.parameters, prob.std_y, device=dev, use_graph=bool(args.graph))
+    opt = set_optimizer("Nadam", K, 0.01, 0.0, 0.9, 0.999, True, 1.0)
+
+    it = 0
+    for _ in range(args.warmup):
+        it += 1
+        K.para_update(it, y, X, Z, opt, verbose=False)
+    fit = K._fit
+    launches_per_step = fit.kernel_launches
+
+    # ---- timed region: K steps, inputs resident in HBM; device time by CUDA events on the path's stream
+    phases = {k: 0.0 for k in ("build", "potrf", "trtri", "uut", "grad")}
+    clocks = ClockSampler(dev)
+    barrier()
+    clocks.start()
+    fit.timer_start()
+    for _ in range(args.steps):
+        it += 1
+        K.para_update(it, y, X, Z, opt, verbose=False)
+        if not args.graph:
+            for k, v in fit.last_timing_ms.items():
+                if k in phases:
+                    phases[k] += v
+    ms_total = fit.timer_stop()
+    barrier()
+    clk = clocks.stop()
+
+    # ---- end to end through the public operator API with HOST buffers: every step copies y, X, Z from
+    # pinned host memory to the device, runs the step and reads parameters, gradients and stats back
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        it += 1
+        K.para_update(it, y, X, Z, opt, verbose=False, reupload=True)
+        par = K.parameters
+        grad = fit.gradients
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    P = par.size
+    h2d = 8 * (y.size + X.size + Z.size)
+    d2h = 8 * (2 * P + 4)
+
+    if dist is not None:
+        t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    n = prob.n
+    ms_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(prob, args.config),
+                       "parallelism": f"{world} independent restart(s), one fit per GPU, no data-path collective",
+                       "l2": "per-step working set 2 x n^2 x 8 B = %.1f GB >> 126 MB L2, no flush needed" % (
+                           2 * n * n * 8 / 1e9),
+                       "launch_mode": "cuda_graph" if args.graph else "eager_streams"},
+            "clocks": clk,
+            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "api": "KernelClass.para_update(iter, y, X, Z, Optim) with host arrays (pinned), "
+                           "parameters + gradients read back every step"},
+            "gpu_launches": launches_per_step * args.steps}
+    # ---- roofline of the dominant kernel (dgemm_nt_kernel, FP64 DMMA): all its launches of one step
+    peaks = _fp64_peak()
+    if not args.graph:
+        dense_ms = (phases["potrf"] + phases["trtri"] + phases["uut"]) / args.steps
+        flops = float(n) ** 3  # n^3/3 each for potrf, trtri, U U^T
+        ach = flops / (dense_ms * 1e-3) * 1e-12
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "dgemm_nt_kernel (FP64 DMMA.8x8x4)", "achieved": ach, "peak": peaks["peak"],
+            "unit": "TFLOP/s", "frac": ach / peaks["peak"], "traffic": None,
+            "peak_source": peaks["source"],
+            "algorithmic_flops_per_step": flops,
+            "note": "all dgemm_nt launches of a step (potrf + trtri + U U^T phases, which also contain the "
+                    "128-wide leaf kernels); CUDA events on the launching stream inside the timed region",
+            "phase_ms": {k: v / args.steps for k, v in phases.items()},
+            "phase_tflops": {k: (flops / 3) / (phases[k] / args.steps * 1e-3) * 1e-12 for k in ("potrf", "trtri", "uut")},
+        }
+    # ---- CPU baseline on the box's host cores (bounded sample)
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        t_full, detail, per_step = cpu_sample(args.config, args.cpu_n, 1, cores)
+        line["cpu_baseline"] = {
+            "value": 1.0 / t_full, "unit": UNIT, "cores": detail["threads"], "kind": "port",
+            "sample": f"1 para_update of the oracle port at n={args.cpu_n} (same p, B, kernel; "
+                      f"{detail['sec_per_iter_at_sample']:.1f} s), stages scaled to n={n}: n^2 for build and "
+                      f"gradient loop, n^3 for dsyevd + V V'",
+            "detail": detail}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _fp64_peak():
+    """FP64 tensor peak: MEASURED_PEAKS.json carries no FP64 figure, so the DMMA issue-rate
+    microbenchmark of this repo (profiles/fp64_peaks_r01.json, measured on this pool's B200) is used."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")) as f:
+            d = json.load(f)
+        return {"peak": d["summary"]["fp64_dmma_peak_tflops"],
+                "source": "profiles/fp64_peaks_r01.json: DMMA.8x8x4 issue-rate microbenchmark on this pool's B200 "
+                          "(MEASURED_PEAKS.json has no FP64 entry); cuBLAS DGEMM on the same box: %.1f" %
+                          d["summary"]["cublas_dgemm_tflops_16384"]}
+    except Exception:
+        return {"peak": 37.0, "source": "nominal B200 FP64 tensor (148 SM x 64 FMA/clk x 1.965 GHz)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--n", type=int, default=None, help="override n (debugging only; invalidates the metric)")
+    ap.add_argument("--cpu-n", type=int, default=1536, help="n of the bounded CPU sample")
+    ap.add_argument("--graph", type=int, default=0, help="1: replay a captured CUDA graph per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,15 @@ int ace_fit_run(ace_fit* fit, int iter_start, int max_iter, double tol, double p
  * parameters; the stored inverse (invKmatn) is left untouched, as in the reference. */
 int ace_fit_get_train_stats(ace_fit* fit, double* stats);
 
+/* Re-upload the training data of an existing handle (same n, p, Bz): what passing y, X, Z to
+ * Kernel$para_update on every call amounts to (R/kernel_SE_R6.R:40).  Any of the three may be NULL. */
+int ace_fit_upload_data(ace_fit* fit, const double* y, const double* X, const double* Z);
+/* Number of CUDA kernel launches one para_update issues (counted from the captured graph). */
+int ace_fit_kernel_launches(ace_fit* fit, int* launches);
+/* CUDA-event stopwatch on the handle's stream: start, ... any calls ..., stop -> device milliseconds. */
+int ace_fit_timer_start(ace_fit* fit);
+int ace_fit_timer_stop(ace_fit* fit, double* ms);
+
 int ace_fit_get_parameters(ace_fit* fit, double* parameters);
 int ace_fit_set_parameters(ace_fit* fit, const double* parameters);
 int ace_fit_get_gradients(ace_fit* fit, double* gradients);      /* last (clipped) gradient vector */
@@ -182,6 +191,10 @@ int ace_dbg_spd_inverse(const double* A, int n, double* L, double* inv, double* 
 /* potrf-only timing on a synthetic SPD matrix generated on the device: returns ms of potrf / trtri / uut
  * averaged over `reps` runs after one warm-up; no host transfer of the matrix. */
 int ace_bench_dense(int n, int reps, double* ms3);
+/* test hooks: stop the triangular-inverse merge after level h; raw state after potrf + trtri
+ * (rawA n_pad x n_pad: X = L^-1 lower / U = L^-T upper; DX, DU: 128 x n_pad diagonal tiles; rawBf workspace) */
+int ace_dbg_set_trtri_max_h(int h);
+int ace_dbg_trtri_raw(const double* A, int n, double* rawA, double* DX, double* DU, double* rawBf);
 
 /* ---------------------------------------------------------------------------------------------
  * O(n) preprocessing, host code as in the reference (same DLL, not on the hot path)
