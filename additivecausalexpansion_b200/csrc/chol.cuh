@@ -16,6 +16,7 @@
 //   Bf        : workspace during phase 2, receives the full symmetric inverse in phase 3
 #pragma once
 #include "dgemm_nt.cuh"
+#include "fastmath.cuh"
 
 namespace ace {
 
@@ -30,7 +31,7 @@ constexpr size_t SMEM_BYTES = (size_t)(128 * LD + 2 * 128 + 2 * 128 + 128 + 128)
 }  // namespace leaf
 
 template <int JB>
-__device__ __forceinline__ void leaf_chol_block(double (&r)[8][8], double* Ls, double* colbuf, double* dg,
+__device__ __forceinline__ void leaf_chol_block(double (&r)[8][8], double* Ls, double* colbuf, double* dg, double* idg,
                                                 int tx, int ty, int* info, int blk) {
   using namespace leaf;
 #pragma unroll 1
@@ -46,20 +47,24 @@ __device__ __forceinline__ void leaf_chol_block(double (&r)[8][8], double* Ls, d
     }
     __syncthreads();
     const double pj = cb[j];
+    // one MUFU-seeded reciprocal square root serves everything on the critical path of this column:
+    // 1/L_jj = y, L_jj = p y, 1/p = y^2 (no IEEE division / sqrt: their latency was ~2/3 of a step)
+    const double inv = fast_rsqrt(pj);
     if (tx == jx) {
-      const double s = sqrt(pj);
-      const double inv = 1.0 / s;
 #pragma unroll
       for (int a = JB; a < 8; ++a) {
         const int i = 16 * a + ty;
         if (i > j) Ls[i + j * LD] = r[a][JB] * inv;
         if (i == j) {
+          double s = pj * inv;
+          s = fma(fma(-s, s, pj), 0.5 * inv, s);
           dg[j] = s;
+          idg[j] = inv;
           if (!(pj > 0.0)) atomicCAS(info, 0, blk * 128 + j + 1);
         }
       }
     }
-    const double invp = 1.0 / pj;
+    const double invp = inv * inv;
 #pragma unroll
     for (int a = JB; a < 8; ++a) {
       const int i = 16 * a + ty;
@@ -140,16 +145,16 @@ __global__ void __launch_bounds__(256, 1) potrf_leaf_kernel(double* __restrict__
     }
   __syncthreads();
 
-  leaf_chol_block<0>(r, Ls, colbuf, dg, tx, ty, info, blk);
-  leaf_chol_block<1>(r, Ls, colbuf, dg, tx, ty, info, blk);
-  leaf_chol_block<2>(r, Ls, colbuf, dg, tx, ty, info, blk);
-  leaf_chol_block<3>(r, Ls, colbuf, dg, tx, ty, info, blk);
-  leaf_chol_block<4>(r, Ls, colbuf, dg, tx, ty, info, blk);
-  leaf_chol_block<5>(r, Ls, colbuf, dg, tx, ty, info, blk);
-  leaf_chol_block<6>(r, Ls, colbuf, dg, tx, ty, info, blk);
-  leaf_chol_block<7>(r, Ls, colbuf, dg, tx, ty, info, blk);
+  leaf_chol_block<0>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
+  leaf_chol_block<1>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
+  leaf_chol_block<2>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
+  leaf_chol_block<3>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
+  leaf_chol_block<4>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
+  leaf_chol_block<5>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
+  leaf_chol_block<6>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
+  leaf_chol_block<7>(r, Ls, colbuf, dg, idg, tx, ty, info, blk);
   __syncthreads();
-  if (threadIdx.x < 128) idg[threadIdx.x] = 1.0 / dg[threadIdx.x];
+  // idg = 1/diag(L) was filled column by column above
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll

@@ -48,6 +48,16 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(y, e2, y);
 }
 
+// x^-1/2 for normal x > 0 (NaN for x <= 0): MUFU seed + cubic step + one quadratic step -> ~1 ulp
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(y * e, fma(0.375, e, 0.5), y);
+  e = fma(-x * y, y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+
 // sqrt(x) for x >= 0 (exact 0 for x == 0): MUFU rsqrt seed + cubic step + one Newton step on the root
 __device__ __forceinline__ double fast_sqrt(double x) {
   double y;
