@@ -171,9 +171,14 @@ static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
     set_error("gradient pass supports p <= 64 and B <= 32");
     return ACE_ERR_UNSUPPORTED;
   }
+  int gpc_max = gk::GROUPS_PER_CTA;
+  if (pl->PD == 20) {  // tuning knobs for the headline shape (p <= 20): terms per thread, b-groups per CTA
+    if (const char* e = std::getenv("ACE_GRAD_BT")) pl->BT = (std::atoi(e) == 2) ? 2 : 3;
+  }
+  if (const char* e = std::getenv("ACE_GRAD_GPC")) gpc_max = std::max(1, std::min(4, std::atoi(e)));
   pl->groups = (B + pl->BT - 1) / pl->BT;
-  pl->gy = (pl->groups + gk::GROUPS_PER_CTA - 1) / gk::GROUPS_PER_CTA;
-  const int gpc = std::min(pl->groups, gk::GROUPS_PER_CTA);
+  const int gpc = std::min(pl->groups, gpc_max);
+  pl->gy = (pl->groups + gpc - 1) / gpc;
   pl->threads = 64 * gpc;
   pl->smem = gk::smem_bytes(pl->PD, B - 1, pl->BT, kind);
   if (pl->smem > 227 * 1024) {
@@ -204,7 +209,7 @@ static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStre
     case 8: return launch_grad_t<8, 8>(a, kind, pl, st);
     case 12: return launch_grad_t<12, 5>(a, kind, pl, st);
     case 16: return launch_grad_t<16, 4>(a, kind, pl, st);
-    case 20: return launch_grad_t<20, 3>(a, kind, pl, st);
+    case 20: return pl.BT == 2 ? launch_grad_t<20, 2>(a, kind, pl, st) : launch_grad_t<20, 3>(a, kind, pl, st);
     case 24: return launch_grad_t<24, 2>(a, kind, pl, st);
     case 32: return launch_grad_t<32, 2>(a, kind, pl, st);
     case 48: return launch_grad_t<48, 1>(a, kind, pl, st);

@@ -65,18 +65,21 @@ __device__ __forceinline__ void leaf_chol_block(double (&r)[8][8], double* Ls, d
       }
     }
     const double invp = inv * inv;
+    // Branch-free rank-1 update of the trailing part held in registers.  Only the block row a == JB and
+    // the block column b == JB straddle the pivot, so only those need a mask; entries above the diagonal
+    // inside diagonal blocks are never read, so no k <= i test at all.
+    double lm[8], cm[8];
 #pragma unroll
     for (int a = JB; a < 8; ++a) {
-      const int i = 16 * a + ty;
-      if (i > j) {
-        const double li = cb[i] * invp;
-#pragma unroll
-        for (int b = JB; b <= a; ++b) {
-          const int k = 16 * b + tx;
-          if (k > j && k <= i) r[a][b] = fma(-li, cb[k], r[a][b]);
-        }
-      }
+      lm[a] = cb[16 * a + ty] * invp;
+      cm[a] = cb[16 * a + tx];
     }
+    lm[JB] = (ty > jx) ? lm[JB] : 0.0;
+    cm[JB] = (tx > jx) ? cm[JB] : 0.0;
+#pragma unroll
+    for (int a = JB; a < 8; ++a)
+#pragma unroll
+      for (int b = JB; b <= a; ++b) r[a][b] = fma(-lm[a], cm[b], r[a][b]);
   }
 }
 
@@ -101,18 +104,18 @@ __device__ __forceinline__ void leaf_inv_block(double (&r)[8][8], double* Ls, do
       }
     }
     __syncthreads();
+    // branch-free: rows i <= j (only possible for a == JB) and columns k > j (only for b == JB) get a zero
+    double lm[8], xm[8];
 #pragma unroll
-    for (int a = JB; a < 8; ++a) {
-      const int i = 16 * a + ty;
-      if (i > j) {
-        const double lij = Ls[i + j * LD];
+    for (int a = JB; a < 8; ++a) lm[a] = Ls[16 * a + ty + j * LD];
+    lm[JB] = (ty > jx) ? lm[JB] : 0.0;
 #pragma unroll
-        for (int b = 0; b <= JB; ++b) {
-          const int k = 16 * b + tx;
-          if (k <= j) r[a][b] = fma(-lij, rb[k], r[a][b]);
-        }
-      }
-    }
+    for (int b = 0; b <= JB; ++b) xm[b] = rb[16 * b + tx];
+    xm[JB] = (tx <= jx) ? xm[JB] : 0.0;
+#pragma unroll
+    for (int a = JB; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b <= JB; ++b) r[a][b] = fma(-lm[a], xm[b], r[a][b]);
   }
 }
 

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256, 1) grad_kernel(const GradArgs a) {
   static_assert(BT <= 16, "BT too large");
   constexpr int NW = nw(BT, KIND);          // distance sums per thread
   constexpr int WP = wp(BT, KIND);          // padded to a multiple of 2 for 16-byte loads
-  constexpr int Q = (PD * (BT + 2) <= 64) ? 2 : 1;  // columns per iteration (register budget)
+  constexpr int Q = (PD * (BT + 2) <= 80 && BT <= 5) ? 2 : 1;  // columns per iteration (register budget)
   extern __shared__ __align__(128) unsigned char smraw[];
   const int p = a.p, B = a.B, Bz = a.B - 1;
   const int ngroups_cta = blockDim.x / 64;  // b-groups handled by this CTA (<= 4)
@@ -296,13 +296,13 @@ __global__ void __launch_bounds__(256, 1) grad_kernel(const GradArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pw = warp & 1;             // which half of the 64 rows
   const int gl = warp >> 1;            // local b-group
-  const int bg = blockIdx.y * GROUPS_PER_CTA + gl;  // global b-group
+  const int bg = blockIdx.y * ngroups_cta + gl;     // global b-group
   const int b0 = bg * BT;
   const int li = pw * 32 + lane;
 
   for (int idx = threadIdx.x; idx < ngroups_cta * PD * WP; idx += blockDim.x) {
     const int g = idx / (PD * WP), r = idx % (PD * WP), d = r / WP, t = r % WP;
-    const int c = (blockIdx.y * GROUPS_PER_CTA + g) * BT + t;  // column of the extended table
+    const int c = (blockIdx.y * ngroups_cta + g) * BT + t;  // column of the extended table
     const bool ok = (t < NW) && (c <= B) && (d < p);
     wgrp[idx] = ok ? a.tab[TAB_WE + d * WSTRIDE + c] : 0.0;
   }
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256, 1) grad_kernel(const GradArgs a) {
   for (int idx = threadIdx.x; idx < ngroups_cta * NV; idx += blockDim.x) {
     const int g = idx / NV, r = idx % NV;
     const double v = red[(2 * g) * NV + r] + red[(2 * g + 1) * NV + r];
-    const int gb0 = (blockIdx.y * GROUPS_PER_CTA + g) * BT;
+    const int gb0 = (blockIdx.y * ngroups_cta + g) * BT;
     if (r < PD * BT) {
       const int d = r / BT, b = gb0 + r % BT;
       if (d < p && b < B) out[2 + B + b + B * d] = v;
