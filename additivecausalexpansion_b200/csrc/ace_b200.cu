@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "chol.cuh"
+#include "nccl_dyn.h"
 #include "gp_kernels.cuh"
 #include "pair_kernels.cuh"
 #include "pred_kernels.cuh"
@@ -232,6 +233,11 @@ struct Core {
   double* h_sc = nullptr;  // pinned: SC_COUNT doubles + info
   GradPlan gp;
   int nchunks = 0;
+  // multi-GPU sharding of ONE fit (ace_fit_shard): rank/world of the communicator, and `red` = [P partial
+  // sums | n_pad entries of K*alpha], the vector that is all-reduced each iteration
+  int shard_rank = 0, shard_world = 1;
+  DBuf<double> red;
+  double* ka() { return red.p ? red.p + P : Ka.p; }
 
   ~Core() {
     if (h_sc) cudaFreeHost(h_sc);
@@ -348,12 +354,30 @@ struct Core {
     return launch_kernmat(a, kind, st);
   }
 
+  // Multi-GPU: this rank's two column blocks of K + e^sigma I (rows >= first column of the block only)
+  int enqueue_build_blocks(double* out) {
+    const int w = shard_block_width(n_pad, shard_world);
+    for (int blk = 0; blk < 2 * shard_world; ++blk) {
+      if (shard_block_owner(blk, shard_world) != shard_rank) continue;
+      const int c0 = blk * w, r0 = c0;
+      KernArgs a{};
+      a.X1 = X.p + r0; a.Z1 = Z.p + r0; a.LZ1 = LZ.p + r0; a.ld1 = n_pad;
+      a.X2 = X.p + c0; a.Z2 = Z.p + c0; a.LZ2 = LZ.p + c0; a.ld2 = n_pad;
+      a.n1 = std::max(0, n - r0); a.n2 = std::max(0, std::min(w, n - c0));
+      a.n1_pad = n_pad - r0; a.n2_pad = w; a.p = p; a.B = B; a.tab = tab.p;
+      a.K = out + r0 + (size_t)c0 * n_pad; a.ldk = n_pad;
+      a.sym = 0; a.add_noise = 1; a.pad_identity = 1; a.row_off = r0; a.col_off = c0;
+      ACE_TRY(launch_kernmat(a, kind, st));
+    }
+    return 0;
+  }
+
   // u = Kinv y, s = Kinv 1, alpha = u - mu s (mu closed form first when asked and iter == 1)
   int enqueue_alpha(const double* Kinv, int set_mu_first_iter) {
     dim3 grid((n_pad + gv::ROWS - 1) / gv::ROWS, nchunks);
     gemv2_kernel<<<grid, gv::ROWS, 0, st>>>(Kinv, n_pad, n, y.p, pu.p, ps.p, n_pad);
     ACE_CUDA(cudaGetLastError());
-    alpha_kernel<<<1, 1024, 0, st>>>(pu.p, ps.p, nchunks, n, n_pad, theta.p, uvec.p, svec.p, alpha.p, Ka.p, sc.p,
+    alpha_kernel<<<1, 1024, 0, st>>>(pu.p, ps.p, nchunks, n, n_pad, theta.p, uvec.p, svec.p, alpha.p, ka(), sc.p,
                                      set_mu_first_iter);
     ACE_CUDA(cudaGetLastError());
     return 0;
@@ -361,15 +385,20 @@ struct Core {
 
   int enqueue_grad(const double* Kinv) {
     GradArgs g{};
-    g.X = X.p; g.Z = Z.p; g.LZ = LZ.p; g.ldx = n_pad; g.Kinv = Kinv; g.ld = n_pad; g.alpha = alpha.p; g.Ka = Ka.p;
+    g.X = X.p; g.Z = Z.p; g.LZ = LZ.p; g.ldx = n_pad; g.Kinv = Kinv; g.ld = n_pad; g.alpha = alpha.p; g.Ka = ka();
     g.tab = tab.p; g.partials = partials.p; g.n = n; g.p = p; g.B = B; g.P = P;
     g.ntiles_side = (n + gk::T - 1) / gk::T;
+    g.tile_rank = shard_rank; g.tile_world = shard_world;
     return launch_grad(g, kind, gp, st);
   }
 
   int enqueue_finalize(const double* Kinv, const ace_fit_config& c, int do_update) {
     FinalizeArgs f{};
-    f.partials = partials.p; f.nparts = gp.gx * gp.gy; f.y = y.p; f.alpha = alpha.p; f.Ka = Ka.p; f.dvec = dvec.p;
+    f.partials = partials.p; f.nparts = gp.gx * gp.gy; f.y = y.p; f.alpha = alpha.p; f.Ka = ka(); f.dvec = dvec.p;
+    if (shard_world > 1) {  // the all-reduced sums live in red[0..P)
+      f.partials = red.p;
+      f.nparts = 1;
+    }
     f.Kinv = Kinv; f.ld = n_pad; f.tab = tab.p; f.theta = theta.p; f.m = m.p; f.v = v.p; f.grad = grad.p; f.sc = sc.p;
     f.n = n; f.p = p; f.B = B; f.P = P; f.kind = kind; f.optimizer = c.optimizer; f.lr = c.learning_rate;
     f.beta1 = c.beta1; f.beta2 = c.beta2; f.eps = 1e-8; f.momentum = c.momentum; f.std_y = c.std_y;
@@ -404,7 +433,9 @@ struct ace_fit {
   cudaGraphExec_t gexec = nullptr;
   double iter_dev = 0.0;  // host shadow of sc[SC_ITER]
   double ms[6] = {0, 0, 0, 0, 0, 0};
+  ncclComm_t comm = nullptr;  // multi-GPU sharded mode
   ~ace_fit() {
+    if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
     if (sw0) cudaEventDestroy(sw0);
     if (sw1) cudaEventDestroy(sw1);
     if (gexec) cudaGraphExecDestroy(gexec);
@@ -417,7 +448,23 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
   DenseWork w = c.dense(c.A.p, c.Bf.p);
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[0], c.st));
   ACE_TRY(c.enqueue_prep());
-  ACE_TRY(c.enqueue_build_sym(c.A.p, 1, nullptr, 0));
+  const bool sharded = c.shard_world > 1;
+  if (!sharded) {
+    ACE_TRY(c.enqueue_build_sym(c.A.p, 1, nullptr, 0));
+  } else {
+    // every rank builds its two column blocks, then the blocks are exchanged over NVLink (one grouped
+    // NCCL broadcast per block); the factorisation below is done redundantly on every rank
+    NcclApi& nc = nccl_api();
+    ACE_TRY(c.enqueue_build_blocks(c.A.p));
+    const int wdt = shard_block_width(c.n_pad, c.shard_world);
+    const size_t cnt = (size_t)wdt * c.n_pad;
+    ACE_NCCL(nc.GroupStart());
+    for (int blk = 0; blk < 2 * c.shard_world; ++blk) {
+      double* ptr = c.A.p + (size_t)blk * cnt;
+      ACE_NCCL(nc.Broadcast(ptr, ptr, cnt, ncclFloat64, shard_block_owner(blk, c.shard_world), f->comm, c.st));
+    }
+    ACE_NCCL(nc.GroupEnd());
+  }
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
   ACE_TRY(potrf_blocked(w));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
@@ -427,6 +474,13 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));
   ACE_TRY(c.enqueue_alpha(c.Bf.p, 1));
   ACE_TRY(c.enqueue_grad(c.Bf.p));
+  if (sharded) {
+    // each rank took every world-th tile: sum its CTA partials, then all-reduce [P sums | K*alpha] so that
+    // every rank finalises with bit-identical inputs (parameters stay in lock-step without a broadcast)
+    partials_reduce_kernel<<<1, 1024, 0, c.st>>>(c.partials.p, c.gp.gx * c.gp.gy, c.P, c.red.p);
+    ACE_CUDA(cudaGetLastError());
+    ACE_NCCL(nccl_api().AllReduce(c.red.p, c.red.p, (size_t)c.P + c.n_pad, ncclFloat64, ncclSum, f->comm, c.st));
+  }
   ACE_TRY(c.enqueue_finalize(c.Bf.p, f->cfg, 1));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[5], c.st));
   return 0;
@@ -603,6 +657,64 @@ int ace_fit_get_train_stats(ace_fit* f, double* stats) {
   stats[0] = c.h_sc[SC_RMSE];
   stats[1] = c.h_sc[SC_EVID];
   if (c.h_info() > 0) return c.h_info();
+  return 0;
+}
+
+int ace_comm_unique_id(char* id128) {
+  if (!id128) return usage("null argument");
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) {
+    set_error(nc.why);
+    return ACE_ERR_UNSUPPORTED;
+  }
+  ncclUniqueId id;
+  ACE_NCCL(nc.GetUniqueId(&id));
+  static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id128, &id, 128);
+  return 0;
+}
+
+int ace_shard_plan(int n, int world, int rank, int* blocks2, int* width) {
+  if (!blocks2 || !width || world < 1 || rank < 0 || rank >= world) return usage("ace_shard_plan: bad argument");
+  const int n_pad = round_up(n, TB);
+  *width = shard_block_width(n_pad, world);
+  if (*width == 0) {
+    set_error("sharding needs ceil(n/128)*128 divisible by 128*world");
+    return ACE_ERR_UNSUPPORTED;
+  }
+  blocks2[0] = rank;
+  blocks2[1] = 2 * world - 1 - rank;
+  return 0;
+}
+
+int ace_fit_shard(ace_fit* f, const char* id128, int rank, int world) {
+  if (!f || !id128 || world < 1 || rank < 0 || rank >= world) return usage("ace_fit_shard: bad argument");
+  if (world == 1) return 0;
+  Core& c = f->c;
+  ACE_CUDA(cudaSetDevice(c.device));
+  if (shard_block_width(c.n_pad, world) == 0) {
+    set_error("sharding needs ceil(n/128)*128 divisible by 128*world");
+    return ACE_ERR_UNSUPPORTED;
+  }
+  NcclApi& nc = nccl_api();
+  if (!nc.ok) {
+    set_error(nc.why);
+    return ACE_ERR_UNSUPPORTED;
+  }
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ACE_NCCL(nc.CommInitRank(&f->comm, world, id, rank));
+  ACE_TRY(c.red.alloc((size_t)c.P + c.n_pad));
+  ACE_CUDA(cudaMemsetAsync(c.red.p, 0, sizeof(double) * ((size_t)c.P + c.n_pad), c.st));
+  c.shard_rank = rank;
+  c.shard_world = world;
+  if (f->gexec) {  // a graph captured before sharding is stale
+    cudaGraphExecDestroy(f->gexec);
+    cudaGraphDestroy(f->graph);
+    f->gexec = nullptr;
+    f->graph = nullptr;
+  }
+  f->launches = -1;
   return 0;
 }
 

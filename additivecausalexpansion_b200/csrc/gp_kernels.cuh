@@ -272,6 +272,16 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const FinalizeArgs a) {
   }
 }
 
+// multi-GPU: sum this rank's per-CTA partial rows into red[0..P) ahead of the all-reduce
+__global__ void __launch_bounds__(1024) partials_reduce_kernel(const double* __restrict__ partials, int nparts, int P,
+                                                               double* __restrict__ red) {
+  for (int k = threadIdx.x; k < P; k += blockDim.x) {
+    double s = 0.0;
+    for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * P + k];
+    red[k] = s;
+  }
+}
+
 // statistics only (stats_cpp, src/stats_cpp.cpp:9-32): needs alpha = Kinv (y - mu) and K alpha
 __global__ void __launch_bounds__(1024) stats_kernel(const double* __restrict__ y, const double* __restrict__ alpha,
                                                      const double* __restrict__ Ka, const double* __restrict__ dvec,

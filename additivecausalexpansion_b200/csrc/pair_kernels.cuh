@@ -59,6 +59,10 @@ struct KernArgs {
   int add_noise;    // sym: K_ii += e^sigma for i < n
   int pad_identity; // sym: rows/cols >= n form an identity block
   int skip0;        // 1: leave the nuisance term b = 0 out of the sum (marginal kernels, src/pred_cpp.cpp:55-63)
+  // rectangular blocks of the TRAINING kernel (multi-GPU column-block sharding): global index of the
+  // block's first row / column, so that the noise diagonal and the identity padding land where they
+  // belong.  Both 0 and add_noise = pad_identity = 0 for ordinary cross kernels.
+  int row_off, col_off;
 };
 
 namespace kb {
@@ -209,7 +213,12 @@ __global__ void __launch_bounds__(256, 2) kernmat_kernel(const KernArgs a) {
       if (a.sym) {
         Tt[li * LDT + jj] = ksum[q];
       } else {
-        a.K[gi + (size_t)gj * a.ldk] = (gi < a.n1 && gj < a.n2) ? ksum[q] : 0.0;
+        double v = (gi < a.n1 && gj < a.n2) ? ksum[q] : 0.0;
+        if (a.row_off + gi == a.col_off + gj) {
+          if (gi < a.n1 && gj < a.n2) v += a.add_noise ? esig : 0.0;
+          else if (a.pad_identity) v = 1.0;
+        }
+        a.K[gi + (size_t)gj * a.ldk] = v;
       }
     }
   }
@@ -256,6 +265,7 @@ struct GradArgs {
   double* partials;  // [gridDim.y * gridDim.x][P]
   int n, p, B, P;
   int ntiles_side;   // ceil(n / 64)
+  int tile_rank, tile_world;  // multi-GPU: this rank takes tiles L = tile_rank (mod tile_world); 0, 1 otherwise
 };
 
 namespace gk {
@@ -330,7 +340,8 @@ __global__ void __launch_bounds__(256, 1) grad_kernel(const GradArgs a) {
   const double* w_mine = wgrp + gl * PD * WP;
   const long ntiles = (long)a.ntiles_side * (a.ntiles_side + 1) / 2;
   uint32_t phase = 0;
-  for (long L = blockIdx.x; L < ntiles; L += gridDim.x) {
+  const long tstride = (long)gridDim.x * a.tile_world;
+  for (long L = (long)blockIdx.x * a.tile_world + a.tile_rank; L < ntiles; L += tstride) {
     long tt = (long)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
     while (tt * (tt + 1) / 2 > L) --tt;
     while ((tt + 1) * (tt + 2) / 2 <= L) ++tt;

@@ -89,6 +89,19 @@ class AceFit:
                                 _p(stats), C.byref(done)), "ace_fit_run")
         return done.value, stats[:, :done.value].copy()
 
+    def shard(self, dist):
+        """Shard this fit over the ranks of an initialised torch.distributed group (one process per GPU):
+        rank 0 creates the NCCL id, it is broadcast as an object, every rank joins (ace_fit_shard)."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if world == 1:
+            return
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            check(lib().ace_comm_unique_id(buf), "ace_comm_unique_id")
+        box = [buf.raw]
+        dist.broadcast_object_list(box, src=0)
+        check(lib().ace_fit_shard(self._h, box[0], rank, world), "ace_fit_shard")
+
     def upload_data(self, y=None, X=None, Z=None):
         """Host -> device copy of the training data (what the per-call y, X, Z arguments of
         Kernel$para_update amount to)."""

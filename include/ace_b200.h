@@ -150,6 +150,18 @@ int ace_fit_run(ace_fit* fit, int iter_start, int max_iter, double tol, double p
  * parameters; the stored inverse (invKmatn) is left untouched, as in the reference. */
 int ace_fit_get_train_stats(ace_fit* fit, double* stats);
 
+/* Multi-GPU sharding of ONE fit over `world` GPUs of a node (one process per GPU):
+ * the kernel build is split into 2*world column blocks (rank r builds blocks r and 2*world-1-r, lower
+ * trapezoids only) that are exchanged with NCCL broadcasts over NVLink; the Cholesky / inverse run
+ * redundantly on every rank; the gradient pass takes every world-th tile and its P sums + K*alpha are
+ * all-reduced, so all ranks hold bit-identical parameters after every iteration.
+ * ace_comm_unique_id: rank 0 creates the 128-byte NCCL id and distributes it out of band;
+ * ace_shard_plan: the two column blocks (of `width` columns of the 128-padded matrix) a rank builds (host only);
+ * ace_fit_shard: every rank joins the communicator; needs ceil(n/128)*128 divisible by 128*world. */
+int ace_comm_unique_id(char* id128);
+int ace_shard_plan(int n, int world, int rank, int* blocks2, int* width);
+int ace_fit_shard(ace_fit* fit, const char* id128, int rank, int world);
+
 /* Re-upload the training data of an existing handle (same n, p, Bz): what passing y, X, Z to
  * Kernel$para_update on every call amounts to (R/kernel_SE_R6.R:40).  Any of the three may be NULL. */
 int ace_fit_upload_data(ace_fit* fit, const double* y, const double* X, const double* Z);

@@ -1,0 +1,27 @@
+"""One fit sharded over 2 GPUs (NCCL) must track the single-GPU fit and keep the ranks bit-identical.
+Needs >= 2 CUDA devices; skipped otherwise (scripts/shard_check.py is the same check under torchrun)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sharded_fit_matches_single_gpu():
+    from additivecausalexpansion_b200 import _lib
+
+    if _lib.lib().ace_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29577", os.path.join(ROOT, "scripts", "shard_check.py"), "C2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["params_bit_identical_across_ranks"]
+    for it in res["iters"]:
+        assert it["evid_rel"] <= 1e-12 and it["grad_rel"] <= 1e-9 and it["par_abs"] <= 1e-10
