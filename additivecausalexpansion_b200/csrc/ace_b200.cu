@@ -17,6 +17,7 @@
 #include "nccl_dyn.h"
 #include "gp_kernels.cuh"
 #include "pair_kernels.cuh"
+#include "grad2_kernel.cuh"
 #include "pred_kernels.cuh"
 
 namespace ace {
@@ -157,6 +158,7 @@ static int launch_kernmat(const KernArgs& a, int kind, cudaStream_t st) {
 struct GradPlan {
   int PD = 0, BT = 0, groups = 0, gy = 0, threads = 0, gx = 0;
   size_t smem = 0;
+  int v2 = 0, PD8 = 0, BD8 = 0;  // second-generation kernel (grad2_kernel.cuh) when the shape is instantiated
 };
 
 static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
@@ -187,7 +189,45 @@ static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
     return ACE_ERR_UNSUPPORTED;
   }
   pl->gx = 2 * sms;
+  // grad2_kernel: one thread per pair for all terms, length-scale sums on the tensor pipe
+  const int PD8 = (p + 7) / 8 * 8, BD8 = (B + 7) / 8 * 8;
+  const char* impl = std::getenv("ACE_GRAD_IMPL");
+  // measured (profiles/r01): grad2 wins for p <= 16 (C2: 0.76 vs 0.88 ms), grad_kernel for p = 20 (C3: 18.9 vs 19.6 ms)
+  const bool want2 = impl ? (std::atoi(impl) == 2) : (p <= 16);
+  if (PD8 <= 32 && BD8 <= 16 && want2) {
+    const size_t sm2 = g2::smem_bytes(PD8, BD8, B - 1);
+    if (sm2 <= 227 * 1024) {
+      pl->v2 = 1; pl->PD8 = PD8; pl->BD8 = BD8; pl->smem = sm2; pl->gy = 1; pl->threads = 256;
+    }
+  }
   return 0;
+}
+
+template <int PD8, int BD8>
+static int launch_grad2_t(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
+  if (kind == 0) {
+    ACE_CUDA(cudaFuncSetAttribute(grad2_kernel<PD8, BD8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    grad2_kernel<PD8, BD8, 0><<<pl.gx, 256, pl.smem, st>>>(a);
+  } else {
+    ACE_CUDA(cudaFuncSetAttribute(grad2_kernel<PD8, BD8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    grad2_kernel<PD8, BD8, 1><<<pl.gx, 256, pl.smem, st>>>(a);
+  }
+  ACE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_grad2(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
+  const int key = pl.PD8 * 100 + pl.BD8;
+  switch (key) {
+    case 808: return launch_grad2_t<8, 8>(a, kind, pl, st);
+    case 816: return launch_grad2_t<8, 16>(a, kind, pl, st);
+    case 1608: return launch_grad2_t<16, 8>(a, kind, pl, st);
+    case 1616: return launch_grad2_t<16, 16>(a, kind, pl, st);
+    case 2408: return launch_grad2_t<24, 8>(a, kind, pl, st);
+    case 2416: return launch_grad2_t<24, 16>(a, kind, pl, st);
+    case 3208: return launch_grad2_t<32, 8>(a, kind, pl, st);
+    default: return launch_grad2_t<32, 16>(a, kind, pl, st);
+  }
 }
 
 template <int PD, int BT>
@@ -204,7 +244,10 @@ static int launch_grad_t(const GradArgs& a, int kind, const GradPlan& pl, cudaSt
   return 0;
 }
 
+static int launch_grad2(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st);
+
 static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
+  if (pl.v2) return launch_grad2(a, kind, pl, st);
   switch (pl.PD) {
     case 4: return launch_grad_t<4, 16>(a, kind, pl, st);
     case 8: return launch_grad_t<8, 8>(a, kind, pl, st);

@@ -35,8 +35,7 @@ __device__ __forceinline__ double term_value(int b, double lam, double D_or_r, d
     const double sr = SQRT3 * D_or_r;
     const double base = (1.0 + sr) * fast_exp(lam - sr);
     if (b == 0) return base;
-    if (z1 == 0.0 || z2 == 0.0) return 0.0;
-    return base * z1 * z2;
+    return base * z1 * z2;  // exactly (+-)0 when a basis value is 0: base is finite, no test needed
   }
 }
 
