@@ -268,8 +268,8 @@ static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStre
 struct Core {
   int device = 0, sms = 148;
   int n = 0, n_pad = 0, p = 0, Bz = 0, B = 0, P = 0, kind = 0;
-  cudaStream_t st = nullptr, side = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t st = nullptr, side = nullptr, aux = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t tev[8] = {};
   DBuf<double> X, Z, LZ, y, theta, m, v, grad, tab, sc, A, Bf, DX, DU, dvec, alpha, uvec, svec, Ka, pu, ps, partials;
   DBuf<int> info;
@@ -290,6 +290,7 @@ struct Core {
       if (e) cudaEventDestroy(e);
     if (st) cudaStreamDestroy(st);
     if (side) cudaStreamDestroy(side);
+    if (aux) cudaStreamDestroy(aux);
   }
 
   int init(int dev, int n_, int p_, int Bz_, int kind_, bool need_dense, bool need_grad) {
@@ -310,6 +311,7 @@ struct Core {
     int lo = 0, hi = 0;
     ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     ACE_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));  // panel stream: high priority
+    ACE_CUDA(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, lo));   // filler work: lowest priority
     for (auto& e : ev) ACE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : tev) ACE_CUDA(cudaEventCreate(&e));
     ACE_CUDA(cudaMallocHost(&h_sc, sizeof(double) * (SC_COUNT + 2)));
@@ -372,7 +374,7 @@ struct Core {
   DenseWork dense(double* Abuf, double* Bbuf) {
     DenseWork w;
     w.A = Abuf; w.ld = n_pad; w.nb = n_pad / TB; w.DX = DX.p; w.DU = DU.p; w.dvec = dvec.p; w.info = info.p;
-    w.Bf = Bbuf; w.main = st; w.side = side;
+    w.Bf = Bbuf; w.main = st; w.side = side; w.aux = aux; w.ev_half = ev[4]; w.ev_aux = ev[5];
     w.ev_panel[0] = ev[0]; w.ev_panel[1] = ev[1]; w.ev_upd[0] = ev[2]; w.ev_upd[1] = ev[3];
     if (const char* e = std::getenv("ACE_PANEL_BLOCKS")) {  // tuning knob (128-blocks per look-ahead panel)
       const int v = std::atoi(e);
@@ -509,9 +511,9 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
     ACE_NCCL(nc.GroupEnd());
   }
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
-  ACE_TRY(potrf_blocked(w));
+  // Cholesky and triangular inverse overlap (potrf_trtri), so they are timed as one phase: ms[1] = both, ms[2] = 0
+  ACE_TRY(potrf_trtri(w));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
-  ACE_TRY(trtri_merge(w));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[3], c.st));
   ACE_TRY(uut_inverse(w));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));

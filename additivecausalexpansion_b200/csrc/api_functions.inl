@@ -507,15 +507,40 @@ int ace_bench_dense(int n, int reps, double* ms3) {
   Core c;
   ACE_TRY(c.init(g_device, n, 1, 1, 0, true, false));
   DenseWork w = c.dense(c.A.p, c.Bf.p);
+  const char* sep = std::getenv("ACE_DENSE_SEPARATE");  // unset/1: potrf and trtri timed separately; 0: overlapped
+  const bool separate = !(sep && std::atoi(sep) == 0);
   double acc[3] = {0, 0, 0};
   for (int r = 0; r <= reps; ++r) {
     const size_t total = (size_t)c.n_pad * c.n_pad;
     synth_spd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(c.A.p, c.n_pad, c.n_pad);
     ACE_CUDA(cudaGetLastError());
+    PotrfTrace tr;
+    const bool tracing = std::getenv("ACE_POTRF_TRACE") && r == reps;
+    if (tracing) {
+      w.trace = &tr;
+      cudaEventCreate(&tr.t0);
+      cudaEventRecord(tr.t0, c.st);
+    }
     ACE_CUDA(cudaEventRecord(c.tev[0], c.st));
-    ACE_TRY(potrf_blocked(w));
-    ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
-    ACE_TRY(trtri_merge(w));
+    if (separate) {
+      ACE_TRY(potrf_blocked(w));
+      if (tracing) {
+        ACE_CUDA(cudaStreamSynchronize(c.st));
+        auto at = [&](cudaEvent_t e) { float t = 0; cudaEventElapsedTime(&t, tr.t0, e); return t; };
+        std::printf("J  panel_begin panel_end | upd_begin upda_end updb_end   (ms since start)\n");
+        for (size_t k = 0; k < tr.panel_begin.size(); ++k) {
+          std::printf("%2zu  %8.3f %8.3f |", k, at(tr.panel_begin[k]), at(tr.panel_end[k]));
+          if (k < tr.upd_begin.size()) std::printf(" %8.3f %8.3f %8.3f", at(tr.upd_begin[k]), at(tr.upda_end[k]), k < tr.updb_end.size() ? at(tr.updb_end[k]) : -1.f);
+          std::printf("\n");
+        }
+        w.trace = nullptr;
+      }
+      ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
+      ACE_TRY(trtri_merge(w));
+    } else {  // production schedule: leading block's inverse overlapped with the potrf tail
+      ACE_TRY(potrf_trtri(w));
+      ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
+    }
     ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
     ACE_TRY(uut_inverse(w));
     ACE_CUDA(cudaEventRecord(c.tev[3], c.st));

@@ -18,6 +18,9 @@
 #include "dgemm_nt.cuh"
 #include "fastmath.cuh"
 
+#include <cstdlib>
+#include <vector>
+
 namespace ace {
 
 // ---------------------------------------------------------------------------------------------
@@ -199,9 +202,11 @@ __global__ void __launch_bounds__(256, 1) potrf_leaf_kernel(double* __restrict__
 // X L^T = P, with DX = L_kk^-1).  One CTA owns 64 full rows, so in-place is race free.
 // ---------------------------------------------------------------------------------------------
 namespace trsml {
-constexpr int ROWS = 64, LDA = ROWS + 4, LDB = 128 + 4;
-constexpr size_t SMEM_BYTES = (size_t)(128 * LDA + 128 * LDB) * 8 + 16;
-constexpr uint32_t TX_BYTES = (128 * ROWS + 128 * 128) * 8;
+constexpr int ROWS = 64, LDA = ROWS + 4, LDB = 128 + 4, KH = 64;
+// A tile (all 128 k) + HALF of DX at a time: 137 KB, so that the kernel can take the slot next to a resident
+// dgemm_nt CTA (77 KB) instead of waiting for a completely empty SM behind the trailing update
+constexpr size_t SMEM_BYTES = (size_t)(128 * LDA + KH * LDB) * 8 + 16;
+constexpr uint32_t TX0_BYTES = (128 * ROWS + KH * 128) * 8, TX1_BYTES = KH * 128 * 8;
 }  // namespace trsml
 
 __global__ void __launch_bounds__(128, 1) trsm_leaf_kernel(double* __restrict__ P, long ld,
@@ -210,23 +215,22 @@ __global__ void __launch_bounds__(128, 1) trsm_leaf_kernel(double* __restrict__ 
   extern __shared__ __align__(128) unsigned char smraw[];
   double* As = reinterpret_cast<double*>(smraw);
   double* Bs = As + 128 * LDA;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(Bs + 128 * LDB);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(Bs + KH * LDB);  // bar[0]: A + DX[:, 0:64), bar[1]: DX[:, 64:128)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* Pr = P + (size_t)blockIdx.x * ROWS;
   if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     fence_mbar_init();
   }
   __syncthreads();
   if (warp == 0) {
-    if (lane == 0) mbar_arrive_expect_tx(bar, TX_BYTES);
+    if (lane == 0) mbar_arrive_expect_tx(&bar[0], TX0_BYTES);
     __syncwarp();
-    for (int kk = lane; kk < 128; kk += 32) {
-      tma_bulk_g2s(As + kk * LDA, Pr + (size_t)kk * ld, ROWS * 8, bar);
-      tma_bulk_g2s(Bs + kk * LDB, DXt + (size_t)kk * 128, 128 * 8, bar);
-    }
+    for (int kk = lane; kk < 128; kk += 32) tma_bulk_g2s(As + kk * LDA, Pr + (size_t)kk * ld, ROWS * 8, &bar[0]);
+    for (int kk = lane; kk < KH; kk += 32) tma_bulk_g2s(Bs + kk * LDB, DXt + (size_t)kk * 128, 128 * 8, &bar[0]);
   }
-  mbar_wait(bar, 0);
+  mbar_wait(&bar[0], 0);
 
   const int g = lane >> 2, tq = lane & 3;
   double acc[8][4][2];
@@ -237,18 +241,33 @@ __global__ void __launch_bounds__(128, 1) trsm_leaf_kernel(double* __restrict__ 
   const double* as = As + g;
   const double* bs = Bs + warp * 32 + g;
   const int ks_end = 8 * (warp + 1);  // DX lower triangular: column j only needs k <= j
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    if (half == 1) {
+      __syncthreads();  // everybody is done with DX[:, 0:64) before it is overwritten
+      if (warp == 0) {
+        if (lane == 0) mbar_arrive_expect_tx(&bar[1], TX1_BYTES);
+        __syncwarp();
+        for (int kk = lane; kk < KH; kk += 32)
+          tma_bulk_g2s(Bs + kk * LDB, DXt + (size_t)(KH + kk) * 128, 128 * 8, &bar[1]);
+      }
+      if (ks_end <= KH / 4) break;  // warps 0 and 1 only need k < 64 (uniform per warp; no later barrier)
+      mbar_wait(&bar[1], 0);
+    }
+    const int ks_lo = half * (KH / 4), ks_hi = min(ks_end, (half + 1) * (KH / 4));
 #pragma unroll 2
-  for (int ks = 0; ks < ks_end; ++ks) {
-    const int k = ks * 4 + tq;
-    double a[8], b[4];
+    for (int ks = ks_lo; ks < ks_hi; ++ks) {
+      const int k = ks * 4 + tq;
+      double a[8], b[4];
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) a[mt] = as[k * LDA + mt * 8];
+      for (int mt = 0; mt < 8; ++mt) a[mt] = as[k * LDA + mt * 8];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) b[nt] = bs[k * LDB + nt * 8];
+      for (int nt = 0; nt < 4; ++nt) b[nt] = bs[(k - half * KH) * LDB + nt * 8];
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt)
+      for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
   }
   const int col0 = warp * 32 + 2 * tq;
 #pragma unroll
@@ -264,6 +283,12 @@ __global__ void __launch_bounds__(128, 1) trsm_leaf_kernel(double* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // Host-side drivers
 // ---------------------------------------------------------------------------------------------
+// optional poor-man's timeline of the look-ahead schedule (ACE_POTRF_TRACE=1 in ace_bench_dense)
+struct PotrfTrace {
+  std::vector<cudaEvent_t> panel_begin, panel_end, upd_begin, upda_end, updb_end;
+  cudaEvent_t t0 = nullptr;
+};
+
 struct DenseWork {
   double* A = nullptr;     // n_pad x n_pad
   long ld = 0;
@@ -273,9 +298,11 @@ struct DenseWork {
   double* dvec = nullptr;  // n_pad
   int* info = nullptr;     // device int: 0, or 1-based index of the first non-positive pivot
   double* Bf = nullptr;    // n_pad x n_pad: workspace, then the inverse
-  cudaStream_t main = nullptr, side = nullptr;
+  cudaStream_t main = nullptr, side = nullptr, aux = nullptr;
   cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
+  cudaEvent_t ev_half = nullptr, ev_aux = nullptr;  // overlap of the leading block's inverse with the potrf tail
   int panel_blocks = 4;    // look-ahead panel width in 128-blocks (512 columns)
+  PotrfTrace* trace = nullptr;
 };
 
 inline int configure_dense_kernels() {
@@ -334,8 +361,15 @@ inline int potrf_rec(const DenseWork& w, int a, int b, cudaStream_t st) {
 //   upd_a(J)  : trailing update restricted to the next panel's block column  (main stream)
 //   upd_b(J)  : the rest of the trailing update                              (main stream)
 // panel(J+1) only waits for upd_a(J), so it overlaps upd_b(J).
-inline int potrf_blocked(const DenseWork& w) {
+inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws);
+
+// fork_at > 0: as soon as the leading fork_at block rows/columns of L are final, their triangular inverse is
+// started on the aux stream (it only touches A[0:fork_at, 0:fork_at], which potrf never reads again); the
+// caller joins on ev_aux.  The tail of a Cholesky is latency bound (a chain of 128-wide leaf kernels with
+// almost no trailing work), so this fills otherwise idle SMs.
+inline int potrf_blocked(const DenseWork& w, int fork_at = 0, int fork_when = 0) {
   const int nb = w.nb, pb = w.panel_blocks;
+  bool forked = false;
   ACE_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int), w.main));
   // fork: side stream joins after everything already queued on main
   ACE_CUDA(cudaEventRecord(w.ev_upd[1], w.main));
@@ -344,26 +378,45 @@ inline int potrf_blocked(const DenseWork& w) {
   for (int j0 = 0; j0 < nb; j0 += pb, ++J) {
     const int j1 = min(j0 + pb, nb), j2 = min(j1 + pb, nb);
     // ---- panel(J) on the side stream
+    auto mark = [&](std::vector<cudaEvent_t>* v, cudaStream_t st) {
+      if (!v) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, st);
+      v->push_back(e);
+    };
+    mark(w.trace ? &w.trace->panel_begin : nullptr, w.side);
     ACE_TRY(potrf_rec(w, j0, j1, w.side));
     ACE_TRY(trsm_rec(w, j1, nb, j0, j1, w.side));
+    mark(w.trace ? &w.trace->panel_end : nullptr, w.side);
     ACE_CUDA(cudaEventRecord(w.ev_panel[J & 1], w.side));
+    if (fork_at > 0 && !forked && j1 >= fork_at && j1 >= fork_when && j1 < nb) {
+      ACE_CUDA(cudaEventRecord(w.ev_half, w.side));
+      ACE_CUDA(cudaStreamWaitEvent(w.aux, w.ev_half, 0));
+      ACE_TRY(trtri_merge_range(w, 0, fork_at, w.aux, w.Bf));
+      ACE_CUDA(cudaEventRecord(w.ev_aux, w.aux));
+      forked = true;
+    }
     if (j1 >= nb) break;
     // ---- trailing update on the main stream
     ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_panel[J & 1], 0));
     const int K = (j1 - j0) * TB;
+    mark(w.trace ? &w.trace->upd_begin : nullptr, w.main);
     // upd_a: rows [j1,nb) x cols [j1,j2)
     ACE_TRY(gemm_plain(w, blkptr(w, j1, j0), blkptr(w, j1, j0), blkptr(w, j1, j1), (nb - j1) * TB,
                        (j2 - j1) * TB, K, -1.0, 1.0, 0, w.main));
+    mark(w.trace ? &w.trace->upda_end : nullptr, w.main);
     ACE_CUDA(cudaEventRecord(w.ev_upd[J & 1], w.main));
     ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_upd[J & 1], 0));
     // upd_b: square block [j2,nb) lower tiles
     if (j2 < nb)
       ACE_TRY(gemm_plain(w, blkptr(w, j2, j0), blkptr(w, j2, j0), blkptr(w, j2, j2), (nb - j2) * TB,
                          (nb - j2) * TB, K, -1.0, 1.0, 1, w.main));
+    mark(w.trace ? &w.trace->updb_end : nullptr, w.main);
   }
   // join
   ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_panel[J & 1], 0));
-  return 0;
+  return forked ? 1 : 0;
 }
 
 // Phase 2: U = L^-T into upper(A) (and X = L^-1 into lower(A)) by bottom-up pairwise merging.
@@ -376,50 +429,79 @@ inline int& dbg_trtri_max_h() {
   return v;
 }
 
-inline int trtri_merge(const DenseWork& w) {
-  const int nb = w.nb;
-  cudaStream_t st = w.main;
-  for (int h = 1; h < nb && h <= dbg_trtri_max_h(); h *= 2) {
-    const int nodes = (nb + 2 * h - 1) / (2 * h);
-    const int s1 = h * TB;
-    // regular nodes (full right child) q = 0 .. nreg-1 in one strided-batched launch, ragged last node alone
-    int nreg = 0;
-    while (nreg < nodes && (nreg * 2 * h + 2 * h) <= nb) ++nreg;
-    for (int pass = 0; pass < 2; ++pass) {
-      int q0, cnt, s2;
-      if (pass == 0) {
-        q0 = 0; cnt = nreg; s2 = s1;
-      } else {
-        q0 = nreg; cnt = nodes - nreg;  // 0 or 1
-        if (cnt == 0) break;
-        const int c = q0 * 2 * h + h;
-        if (c >= nb) break;  // lone left child, nothing to merge
-        s2 = (nb - c) * TB;
-      }
-      if (cnt == 0) continue;
-      const int a = q0 * 2 * h, c = a + h;
-      const long node_stride = (long)2 * h * TB * (w.ld + 1);
-      double* Wt = w.Bf + (size_t)q0 * s1 * s1;
-      GemmNT p{};
-      p.A = blkptr(w, a, a); p.lda = w.ld; p.a_tri = 1; p.Adiag = w.DU + (size_t)a * TB * TB;
-      p.B = blkptr(w, c, a); p.ldb = w.ld;
-      p.C = Wt; p.ldc = s1;
-      p.M = s1; p.N = s2; p.K = s1; p.alpha = 1.0; p.beta = 0.0;
-      p.batch = cnt; p.sA = node_stride; p.sB = node_stride; p.sC = (long)s1 * s1;
-      p.sAdiag = (long)2 * h * TB * TB;
-      ACE_TRY(launch_gemm_nt(p, st));
-      GemmNT r{};
-      r.A = blkptr(w, c, c); r.lda = w.ld; r.a_tri = 2; r.Adiag = w.DX + (size_t)c * TB * TB;
-      r.B = Wt; r.ldb = s1;
-      r.C = blkptr(w, c, a); r.ldc = w.ld;
-      r.Ct = blkptr(w, a, c); r.ldct = w.ld;
-      r.M = s2; r.N = s1; r.K = s2; r.alpha = -1.0; r.beta = 0.0;
-      r.batch = cnt; r.sA = node_stride; r.sB = (long)s1 * s1; r.sC = node_stride; r.sCt = node_stride;
-      r.sAdiag = (long)2 * h * TB * TB;
-      ACE_TRY(launch_gemm_nt(r, st));
+// one level (child size h) of the merges lying inside the block range [lo, lo + len)
+inline int trtri_level(const DenseWork& w, int lo, int len, int h, cudaStream_t st, double* ws) {
+  const int nodes = (len + 2 * h - 1) / (2 * h);
+  const int s1 = h * TB;
+  // regular nodes (full right child) q = 0 .. nreg-1 in one strided-batched launch, ragged last node alone
+  int nreg = 0;
+  while (nreg < nodes && (nreg * 2 * h + 2 * h) <= len) ++nreg;
+  for (int pass = 0; pass < 2; ++pass) {
+    int q0, cnt, s2;
+    if (pass == 0) {
+      q0 = 0; cnt = nreg; s2 = s1;
+    } else {
+      q0 = nreg; cnt = nodes - nreg;  // 0 or 1
+      if (cnt == 0) break;
+      const int c_local = q0 * 2 * h + h;
+      if (c_local >= len) break;  // lone left child, nothing to merge
+      s2 = (len - c_local) * TB;
     }
+    if (cnt == 0) continue;
+    const int a = lo + q0 * 2 * h, c = a + h;
+    const long node_stride = (long)2 * h * TB * (w.ld + 1);
+    double* Wt = ws + (size_t)q0 * s1 * s1;
+    GemmNT p{};
+    p.A = blkptr(w, a, a); p.lda = w.ld; p.a_tri = 1; p.Adiag = w.DU + (size_t)a * TB * TB;
+    p.B = blkptr(w, c, a); p.ldb = w.ld;
+    p.C = Wt; p.ldc = s1;
+    p.M = s1; p.N = s2; p.K = s1; p.alpha = 1.0; p.beta = 0.0;
+    p.batch = cnt; p.sA = node_stride; p.sB = node_stride; p.sC = (long)s1 * s1;
+    p.sAdiag = (long)2 * h * TB * TB;
+    ACE_TRY(launch_gemm_nt(p, st));
+    GemmNT r{};
+    r.A = blkptr(w, c, c); r.lda = w.ld; r.a_tri = 2; r.Adiag = w.DX + (size_t)c * TB * TB;
+    r.B = Wt; r.ldb = s1;
+    r.C = blkptr(w, c, a); r.ldc = w.ld;
+    r.Ct = blkptr(w, a, c); r.ldct = w.ld;
+    r.M = s2; r.N = s1; r.K = s2; r.alpha = -1.0; r.beta = 0.0;
+    r.batch = cnt; r.sA = node_stride; r.sB = (long)s1 * s1; r.sC = node_stride; r.sCt = node_stride;
+    r.sAdiag = (long)2 * h * TB * TB;
+    ACE_TRY(launch_gemm_nt(r, st));
   }
   return 0;
+}
+
+// all levels of the merges inside [lo, hi); workspace need <= ((hi - lo) * 128 / 2)^2 doubles
+inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws) {
+  for (int h = 1; h < hi - lo && h <= dbg_trtri_max_h(); h *= 2) ACE_TRY(trtri_level(w, lo, hi - lo, h, st, ws));
+  return 0;
+}
+
+inline int trtri_merge(const DenseWork& w) { return trtri_merge_range(w, 0, w.nb, w.main, w.Bf); }
+
+// Phases 1 + 2 with the inverse of the leading h_top x h_top block (h_top = largest power of two < nb, the
+// left child of the top-level merge) overlapped with the latency-bound tail of the Cholesky.
+inline int potrf_trtri(const DenseWork& w) {
+  const int nb = w.nb;
+  int h_top = 1;
+  while (2 * h_top < nb) h_top *= 2;
+  if (nb < 8 || w.aux == nullptr || dbg_trtri_max_h() < (1 << 30)) {
+    int s = potrf_blocked(w);
+    if (s < 0) return s;
+    return trtri_merge(w);
+  }
+  // the leading block is final after panel h_top/pb, but its inverse is only released once the trailing
+  // updates have become small (last ~quarter of the columns): released earlier it merely competes with them
+  double frac = 0.75;
+  if (const char* e = std::getenv("ACE_FORK_FRAC")) frac = std::atof(e);
+  const int forked = potrf_blocked(w, h_top, (int)(frac * nb));
+  if (forked < 0) return forked;
+  const size_t left_ws = (size_t)(h_top * TB / 2) * (h_top * TB / 2);
+  if (!forked) ACE_TRY(trtri_merge_range(w, 0, h_top, w.main, w.Bf));
+  ACE_TRY(trtri_merge_range(w, h_top, nb, w.main, w.Bf + left_ws));   // right child, own workspace region
+  if (forked) ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_aux, 0));
+  return trtri_level(w, 0, nb, h_top, w.main, w.Bf);                   // top-level merge
 }
 
 // Phase 3: inverse = U * U^T into Bf (both triangles), one launch.
@@ -434,8 +516,7 @@ inline int uut_inverse(const DenseWork& w) {
 }
 
 inline int spd_inverse(const DenseWork& w) {
-  ACE_TRY(potrf_blocked(w));
-  ACE_TRY(trtri_merge(w));
+  ACE_TRY(potrf_trtri(w));
   return uut_inverse(w);
 }
 

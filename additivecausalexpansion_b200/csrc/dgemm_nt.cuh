@@ -12,8 +12,9 @@
 // Padding (ld = 128+4 / 64+4 doubles) makes the DMMA fragment loads bank-conflict free.
 //
 // CTA = 128 x 64 output tile, 4 consumer warps (2 x 2, each 64 x 32 = 8 x 4 DMMA.8x8x4 tiles, 64
-// FP64 accumulators per thread) + 1 producer warp; 4-stage mbarrier full/empty ring; 2 CTAs per SM
-// (100 KB smem, <= 200 regs) so one CTA's C read-modify-write epilogue hides under the other's
+// FP64 accumulators per thread) + 1 producer warp; 3-stage mbarrier full/empty ring; 2 CTAs per SM
+// (77 KB smem each -- a third slot of >= 138 KB stays free for the latency-critical leaf kernels of the
+// Cholesky look-ahead stream --, <= 200 regs) so one CTA's C read-modify-write epilogue hides under the other's
 // main loop.  FP64 has no tcgen05/TMEM kind on Blackwell: DMMA via mma.sync is the FP64 tensor path.
 //
 // All of M, N, K are multiples of 128 (callers pad to the 128-tile grid with identity), so there
@@ -45,7 +46,7 @@ struct GemmNT {
 };
 
 namespace gemm {
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3;
 constexpr int LDAS = BM + 4, LDBS = BN + 4;
 constexpr int A_STAGE = BK * LDAS, B_STAGE = BK * LDBS;  // doubles
 constexpr int CONSUMER_WARPS = 4;
