@@ -269,7 +269,9 @@ struct Core {
   int device = 0, sms = 148;
   int n = 0, n_pad = 0, p = 0, Bz = 0, B = 0, P = 0, kind = 0;
   cudaStream_t st = nullptr, side = nullptr, aux = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  DBuf<double> Wp0, Wp1, Wsmall;  // fused panel TRSM workspaces (chol.cuh)
+  int panel_blocks = 4;
   cudaEvent_t tev[8] = {};
   DBuf<double> X, Z, LZ, y, theta, m, v, grad, tab, sc, A, Bf, DX, DU, dvec, alpha, uvec, svec, Ka, pu, ps, partials;
   DBuf<int> info;
@@ -338,6 +340,20 @@ struct Core {
       ACE_TRY(DX.alloc(N * TB));
       ACE_TRY(DU.alloc(N * TB));
       ACE_TRY(dvec.alloc(N));
+      if (const char* e = std::getenv("ACE_PANEL_BLOCKS")) {  // tuning knob (128-blocks per look-ahead panel)
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 64) panel_blocks = v;
+      }
+      const char* fu = std::getenv("ACE_FUSED_TRSM");
+      const bool pow2 = (panel_blocks & (panel_blocks - 1)) == 0;
+      // measured: the fused panel TRSM pays off from n ~ 12k (16384: 54.2 -> 53.2 ms, 32768: 359 -> 355 ms) and
+      // costs ~0.4 ms below (8192: 13.3 -> 13.8 ms), so it is on for n_pad >= 12288 unless ACE_FUSED_TRSM says otherwise
+      const bool want = fu ? (std::atoi(fu) != 0) : (n_pad >= 12288);
+      if (pow2 && panel_blocks >= 2 && want) {
+        ACE_TRY(Wp0.alloc(N * panel_blocks * TB));
+        ACE_TRY(Wp1.alloc(N * panel_blocks * TB));
+        ACE_TRY(Wsmall.alloc((size_t)(panel_blocks * TB / 2) * (panel_blocks * TB / 2)));
+      }
     }
     if (need_grad) {
       ACE_TRY(plan_grad(p, B, kind, sms, &gp));
@@ -371,15 +387,16 @@ struct Core {
     return 0;
   }
 
-  DenseWork dense(double* Abuf, double* Bbuf) {
+  DenseWork dense(double* Abuf, double* Bbuf, bool allow_fused = true) {
     DenseWork w;
+    w.panel_blocks = panel_blocks;
+    if (allow_fused && Wp0.p) {
+      w.Wp[0] = Wp0.p; w.Wp[1] = Wp1.p; w.Wsmall = Wsmall.p; w.ev_copy[0] = ev[6]; w.ev_copy[1] = ev[7];
+    }
     w.A = Abuf; w.ld = n_pad; w.nb = n_pad / TB; w.DX = DX.p; w.DU = DU.p; w.dvec = dvec.p; w.info = info.p;
     w.Bf = Bbuf; w.main = st; w.side = side; w.aux = aux; w.ev_half = ev[4]; w.ev_aux = ev[5];
     w.ev_panel[0] = ev[0]; w.ev_panel[1] = ev[1]; w.ev_upd[0] = ev[2]; w.ev_upd[1] = ev[3];
-    if (const char* e = std::getenv("ACE_PANEL_BLOCKS")) {  // tuning knob (128-blocks per look-ahead panel)
-      const int v = std::atoi(e);
-      if (v >= 1 && v <= 64) w.panel_blocks = v;
-    }
+
     return w;
   }
 

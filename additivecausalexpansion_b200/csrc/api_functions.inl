@@ -451,7 +451,7 @@ int ace_dbg_spd_inverse(const double* A, int n, double* L, double* inv, double* 
   ACE_TRY(upload_matrix(c.A.p, c.n_pad, c.n_pad, A, n, n, c.st));
   if (c.n_pad > n) pad_identity_kernel<<<(c.n_pad - n + 255) / 256, 256, 0, c.st>>>(c.A.p, c.n_pad, n, c.n_pad);
   ACE_CUDA(cudaGetLastError());
-  DenseWork w = c.dense(c.A.p, c.Bf.p);
+  DenseWork w = c.dense(c.A.p, c.Bf.p, /*allow_fused=*/false);  // L itself is an output here
   ACE_CUDA(cudaEventRecord(c.tev[0], c.st));
   ACE_TRY(potrf_blocked(w));
   ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
@@ -490,7 +490,7 @@ int ace_dbg_trtri_raw(const double* A, int n, double* rawA, double* DXo, double*
   ACE_TRY(c.init(g_device, n, 1, 1, 0, true, false));
   ACE_TRY(upload_matrix(c.A.p, c.n_pad, c.n_pad, A, n, n, c.st));
   if (c.n_pad > n) pad_identity_kernel<<<(c.n_pad - n + 255) / 256, 256, 0, c.st>>>(c.A.p, c.n_pad, n, c.n_pad);
-  DenseWork w = c.dense(c.A.p, c.Bf.p);
+  DenseWork w = c.dense(c.A.p, c.Bf.p, /*allow_fused=*/false);
   ACE_TRY(potrf_blocked(w));
   ACE_TRY(trtri_merge(w));
   ACE_CUDA(cudaStreamSynchronize(c.st));

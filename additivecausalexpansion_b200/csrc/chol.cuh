@@ -303,6 +303,13 @@ struct DenseWork {
   cudaEvent_t ev_half = nullptr, ev_aux = nullptr;  // overlap of the leading block's inverse with the potrf tail
   int panel_blocks = 4;    // look-ahead panel width in 128-blocks (512 columns)
   PotrfTrace* trace = nullptr;
+  // fused panel TRSM (production path): after a diagonal block is factored its inverse X_JJ is formed at once
+  // (the first log2(panel) merge levels of phase 2, done early) and the rows below are solved by ONE GEMM
+  // P X_JJ^T into Wp[J&1] instead of a chain of 7 slot-starved 128-wide kernels; the trailing update reads the
+  // panel from Wp, a copy back into A follows off the critical path (aux stream).
+  double* Wp[2] = {nullptr, nullptr};  // n_pad x (panel_blocks*128) each, ld = n_pad
+  double* Wsmall = nullptr;            // (panel_blocks*128/2)^2 doubles: workspace of the early merges
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
 };
 
 inline int configure_dense_kernels() {
@@ -361,7 +368,7 @@ inline int potrf_rec(const DenseWork& w, int a, int b, cudaStream_t st) {
 //   upd_a(J)  : trailing update restricted to the next panel's block column  (main stream)
 //   upd_b(J)  : the rest of the trailing update                              (main stream)
 // panel(J+1) only waits for upd_a(J), so it overlaps upd_b(J).
-inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws);
+inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws, int h_min = 1);
 
 // fork_at > 0: as soon as the leading fork_at block rows/columns of L are final, their triangular inverse is
 // started on the aux stream (it only touches A[0:fork_at, 0:fork_at], which potrf never reads again); the
@@ -387,13 +394,36 @@ inline int potrf_blocked(const DenseWork& w, int fork_at = 0, int fork_when = 0)
     };
     mark(w.trace ? &w.trace->panel_begin : nullptr, w.side);
     ACE_TRY(potrf_rec(w, j0, j1, w.side));
-    ACE_TRY(trsm_rec(w, j1, nb, j0, j1, w.side));
+    const bool fused = (w.Wp[0] != nullptr);
+    const double* panel = blkptr(w, j1 < nb ? j1 : j0, j0);  // operand of the trailing update
+    if (!fused) {
+      ACE_TRY(trsm_rec(w, j1, nb, j0, j1, w.side));
+    } else {
+      ACE_TRY(trtri_merge_range(w, j0, j1, w.side, w.Wsmall));  // X_JJ (lower blocks of the diagonal block) + U_JJ
+      if (j1 < nb) {
+        if (J >= 2) ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_copy[J & 1], 0));  // Wp[J&1] free again
+        GemmNT t{};
+        t.A = blkptr(w, j1, j0); t.lda = w.ld;
+        t.B = blkptr(w, j0, j0); t.ldb = w.ld; t.b_tri = 2; t.Bdiag = w.DX + (size_t)j0 * TB * TB;
+        t.C = w.Wp[J & 1] + (size_t)j1 * TB; t.ldc = w.ld;
+        t.M = (nb - j1) * TB; t.N = (j1 - j0) * TB; t.K = (j1 - j0) * TB; t.alpha = 1.0; t.beta = 0.0;
+        ACE_TRY(launch_gemm_nt(t, w.side));
+        panel = w.Wp[J & 1] + (size_t)j1 * TB;
+      }
+    }
     mark(w.trace ? &w.trace->panel_end : nullptr, w.side);
     ACE_CUDA(cudaEventRecord(w.ev_panel[J & 1], w.side));
+    if (fused && j1 < nb) {  // solved panel back into A (phase 2 reads it as L21), off the critical path
+      ACE_CUDA(cudaStreamWaitEvent(w.aux, w.ev_panel[J & 1], 0));
+      ACE_CUDA(cudaMemcpy2DAsync(blkptr(w, j1, j0), sizeof(double) * w.ld, w.Wp[J & 1] + (size_t)j1 * TB,
+                                 sizeof(double) * w.ld, sizeof(double) * (size_t)(nb - j1) * TB, (size_t)(j1 - j0) * TB,
+                                 cudaMemcpyDeviceToDevice, w.aux));
+      ACE_CUDA(cudaEventRecord(w.ev_copy[J & 1], w.aux));
+    }
     if (fork_at > 0 && !forked && j1 >= fork_at && j1 >= fork_when && j1 < nb) {
       ACE_CUDA(cudaEventRecord(w.ev_half, w.side));
       ACE_CUDA(cudaStreamWaitEvent(w.aux, w.ev_half, 0));
-      ACE_TRY(trtri_merge_range(w, 0, fork_at, w.aux, w.Bf));
+      ACE_TRY(trtri_merge_range(w, 0, fork_at, w.aux, w.Bf, w.Wp[0] ? w.panel_blocks : 1));
       ACE_CUDA(cudaEventRecord(w.ev_aux, w.aux));
       forked = true;
     }
@@ -403,19 +433,22 @@ inline int potrf_blocked(const DenseWork& w, int fork_at = 0, int fork_when = 0)
     const int K = (j1 - j0) * TB;
     mark(w.trace ? &w.trace->upd_begin : nullptr, w.main);
     // upd_a: rows [j1,nb) x cols [j1,j2)
-    ACE_TRY(gemm_plain(w, blkptr(w, j1, j0), blkptr(w, j1, j0), blkptr(w, j1, j1), (nb - j1) * TB,
-                       (j2 - j1) * TB, K, -1.0, 1.0, 0, w.main));
+    ACE_TRY(gemm_plain(w, panel, panel, blkptr(w, j1, j1), (nb - j1) * TB, (j2 - j1) * TB, K, -1.0, 1.0, 0, w.main));
     mark(w.trace ? &w.trace->upda_end : nullptr, w.main);
     ACE_CUDA(cudaEventRecord(w.ev_upd[J & 1], w.main));
     ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_upd[J & 1], 0));
     // upd_b: square block [j2,nb) lower tiles
     if (j2 < nb)
-      ACE_TRY(gemm_plain(w, blkptr(w, j2, j0), blkptr(w, j2, j0), blkptr(w, j2, j2), (nb - j2) * TB,
-                         (nb - j2) * TB, K, -1.0, 1.0, 1, w.main));
+      ACE_TRY(gemm_plain(w, panel + (size_t)(j2 - j1) * TB, panel + (size_t)(j2 - j1) * TB, blkptr(w, j2, j2),
+                         (nb - j2) * TB, (nb - j2) * TB, K, -1.0, 1.0, 1, w.main));
     mark(w.trace ? &w.trace->updb_end : nullptr, w.main);
   }
   // join
   ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_panel[J & 1], 0));
+  if (w.Wp[0] != nullptr && J >= 1) {
+    ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_copy[0], 0));
+    if (J >= 2) ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_copy[1], 0));
+  }
   return forked ? 1 : 0;
 }
 
@@ -473,12 +506,15 @@ inline int trtri_level(const DenseWork& w, int lo, int len, int h, cudaStream_t 
 }
 
 // all levels of the merges inside [lo, hi); workspace need <= ((hi - lo) * 128 / 2)^2 doubles
-inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws) {
-  for (int h = 1; h < hi - lo && h <= dbg_trtri_max_h(); h *= 2) ACE_TRY(trtri_level(w, lo, hi - lo, h, st, ws));
+inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws, int h_min) {
+  for (int h = h_min; h < hi - lo && h <= dbg_trtri_max_h(); h *= 2) ACE_TRY(trtri_level(w, lo, hi - lo, h, st, ws));
   return 0;
 }
 
-inline int trtri_merge(const DenseWork& w) { return trtri_merge_range(w, 0, w.nb, w.main, w.Bf); }
+// levels below the panel width were already merged panel by panel when the fused panel TRSM is on
+inline int trtri_hmin(const DenseWork& w) { return w.Wp[0] ? w.panel_blocks : 1; }
+
+inline int trtri_merge(const DenseWork& w) { return trtri_merge_range(w, 0, w.nb, w.main, w.Bf, trtri_hmin(w)); }
 
 // Phases 1 + 2 with the inverse of the leading h_top x h_top block (h_top = largest power of two < nb, the
 // left child of the top-level merge) overlapped with the latency-bound tail of the Cholesky.
@@ -498,8 +534,8 @@ inline int potrf_trtri(const DenseWork& w) {
   const int forked = potrf_blocked(w, h_top, (int)(frac * nb));
   if (forked < 0) return forked;
   const size_t left_ws = (size_t)(h_top * TB / 2) * (h_top * TB / 2);
-  if (!forked) ACE_TRY(trtri_merge_range(w, 0, h_top, w.main, w.Bf));
-  ACE_TRY(trtri_merge_range(w, h_top, nb, w.main, w.Bf + left_ws));   // right child, own workspace region
+  if (!forked) ACE_TRY(trtri_merge_range(w, 0, h_top, w.main, w.Bf, trtri_hmin(w)));
+  ACE_TRY(trtri_merge_range(w, h_top, nb, w.main, w.Bf + left_ws, trtri_hmin(w)));   // right child, own workspace region
   if (forked) ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_aux, 0));
   return trtri_level(w, 0, nb, h_top, w.main, w.Bf);                   // top-level merge
 }

@@ -38,6 +38,7 @@ struct GemmNT {
   int M, N, K;
   int a_tri;            // 0: A dense.  1: A upper triangular on the 128-block grid (k starts at the row
                         //    block).  2: A lower triangular (k ends with the row block).
+  int b_tri;            // 2: B lower triangular on the 128-block grid (k ends with the column's block)
   int lower_only;       // 1: C is square, only tiles that intersect i >= j are computed (SYRK)
   double alpha, beta;
   // strided batch (blockIdx.y): problem q uses every pointer advanced by q * its stride (elements)
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
   int k_begin = 0, k_end = p.K;
   if (p.a_tri == 1) k_begin = i0;
   if (p.a_tri == 2) k_end = i0 + BM;
+  if (p.b_tri == 2) k_end = min(k_end, (j0 / TB + 1) * TB);
   const int nchunks = (k_end - k_begin) / BK;
 
   if (threadIdx.x == 0) {
