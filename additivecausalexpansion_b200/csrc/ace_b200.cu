@@ -15,6 +15,7 @@
 
 #include "chol.cuh"
 #include "nccl_dyn.h"
+#include "shard_dense.cuh"
 #include "gp_kernels.cuh"
 #include "pair_kernels.cuh"
 #include "grad2_kernel.cuh"
@@ -283,6 +284,41 @@ struct Core {
   int shard_rank = 0, shard_world = 1;
   DBuf<double> red;
   double* ka() { return red.p ? red.p + P : Ka.p; }
+  // sharded dense phases (shard_dense.cuh): triangular inverse split by levels, K^-1 tiles dealt round-robin
+  bool shard_dense = false;    // on by default for a sharded fit (ACE_SHARD_DENSE=0: redundant dense phases)
+  bool shard_emulate = false;  // one process plays all ranks in turn (single-GPU tests), no NCCL
+  int shard_hmin = 16;
+  bool kinv_partial = false;   // Bf holds only this rank's tiles of K^-1 (U is complete in A)
+  DBuf<double> tvy, tv1, pdg, kdg;
+  int rank_lo() const { return shard_emulate ? 0 : shard_rank; }
+  int rank_hi() const { return shard_emulate ? shard_world : shard_rank + 1; }
+  ShardCtx shard_ctx(ncclComm_t comm) const {
+    ShardCtx cx;
+    cx.rank = shard_rank; cx.world = shard_world; cx.emulate = shard_emulate; cx.comm = comm; cx.h_min = shard_hmin;
+    return cx;
+  }
+  int alloc_shard() {
+    ACE_TRY(red.alloc((size_t)P + n_pad));
+    ACE_CUDA(cudaMemsetAsync(red.p, 0, sizeof(double) * ((size_t)P + n_pad), st));
+    const char* e = std::getenv("ACE_SHARD_DENSE");
+    shard_dense = e ? (std::atoi(e) != 0) : true;
+    if (const char* h = std::getenv("ACE_SHARD_HMIN")) shard_hmin = std::max(1, std::atoi(h));
+    if (shard_dense) {
+      ACE_TRY(tvy.alloc(n_pad));
+      ACE_TRY(tv1.alloc(n_pad));
+      ACE_TRY(pdg.alloc((size_t)n_pad * nchunks));
+      ACE_TRY(kdg.alloc(n_pad));
+    }
+    return 0;
+  }
+  // the full inverse from the replicated U (consumers outside the iteration: invKmatn download, posterior)
+  int ensure_full_inverse() {
+    if (!kinv_partial) return 0;
+    DenseWork w = dense(A.p, Bf.p);
+    ACE_TRY(uut_inverse(w));
+    kinv_partial = false;
+    return 0;
+  }
 
   ~Core() {
     if (h_sc) cudaFreeHost(h_sc);
@@ -420,7 +456,8 @@ struct Core {
   int enqueue_build_blocks(double* out) {
     const int w = shard_block_width(n_pad, shard_world);
     for (int blk = 0; blk < 2 * shard_world; ++blk) {
-      if (shard_block_owner(blk, shard_world) != shard_rank) continue;
+      const int owner = shard_block_owner(blk, shard_world);
+      if (owner < rank_lo() || owner >= rank_hi()) continue;
       const int c0 = blk * w, r0 = c0;
       KernArgs a{};
       a.X1 = X.p + r0; a.Z1 = Z.p + r0; a.LZ1 = LZ.p + r0; a.ld1 = n_pad;
@@ -445,22 +482,39 @@ struct Core {
     return 0;
   }
 
-  int enqueue_grad(const double* Kinv) {
+  // sharded inverse: u = U (U^T y), s = U (U^T 1), diag(K^-1) from the replicated U (upper(Afac) + DU tiles)
+  int enqueue_alpha_tri(const double* Afac, int set_mu_first_iter) {
+    utv2_kernel<<<(n_pad + 7) / 8, 256, 0, st>>>(Afac, n_pad, DU.p, n, n_pad, y.p, tvy.p, tv1.p);
+    ACE_CUDA(cudaGetLastError());
+    dim3 grid((n_pad + gv::ROWS - 1) / gv::ROWS, nchunks);
+    uv2_kernel<<<grid, gv::ROWS, 0, st>>>(Afac, n_pad, DU.p, n_pad, tvy.p, tv1.p, pu.p, ps.p, pdg.p);
+    ACE_CUDA(cudaGetLastError());
+    alpha_kernel<<<1, 1024, 0, st>>>(pu.p, ps.p, nchunks, n, n_pad, theta.p, uvec.p, svec.p, alpha.p, ka(), sc.p,
+                                     set_mu_first_iter, pdg.p, kdg.p);
+    ACE_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  // tile_world 1: all lower tiles.  Otherwise every world-th tile; tile_mode 1 follows the ownership of the
+  // sharded U U^T launch (the rank only reads entries of K^-1 it computed itself).
+  int enqueue_grad(const double* Kinv, int tile_rank = 0, int tile_world = 1, int tile_mode = 0) {
     GradArgs g{};
     g.X = X.p; g.Z = Z.p; g.LZ = LZ.p; g.ldx = n_pad; g.Kinv = Kinv; g.ld = n_pad; g.alpha = alpha.p; g.Ka = ka();
     g.tab = tab.p; g.partials = partials.p; g.n = n; g.p = p; g.B = B; g.P = P;
     g.ntiles_side = (n + gk::T - 1) / gk::T;
-    g.tile_rank = shard_rank; g.tile_world = shard_world;
+    g.tile_rank = tile_rank; g.tile_world = tile_world; g.tile_mode = tile_mode; g.gemm_rows = n_pad / TB;
     return launch_grad(g, kind, gp, st);
   }
 
-  int enqueue_finalize(const double* Kinv, const ace_fit_config& c, int do_update) {
+  int enqueue_finalize(const double* Kinv, const ace_fit_config& c, int do_update, bool reduced = false,
+                       const double* kdiag = nullptr) {
     FinalizeArgs f{};
     f.partials = partials.p; f.nparts = gp.gx * gp.gy; f.y = y.p; f.alpha = alpha.p; f.Ka = ka(); f.dvec = dvec.p;
-    if (shard_world > 1) {  // the all-reduced sums live in red[0..P)
+    if (reduced) {  // sharded iteration: the all-reduced sums live in red[0..P)
       f.partials = red.p;
       f.nparts = 1;
     }
+    f.kdiag = kdiag;
     f.Kinv = Kinv; f.ld = n_pad; f.tab = tab.p; f.theta = theta.p; f.m = m.p; f.v = v.p; f.grad = grad.p; f.sc = sc.p;
     f.n = n; f.p = p; f.B = B; f.P = P; f.kind = kind; f.optimizer = c.optimizer; f.lr = c.learning_rate;
     f.beta1 = c.beta1; f.beta2 = c.beta2; f.eps = 1e-8; f.momentum = c.momentum; f.std_y = c.std_y;
@@ -511,39 +565,63 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[0], c.st));
   ACE_TRY(c.enqueue_prep());
   const bool sharded = c.shard_world > 1;
+  const bool comm = sharded && !c.shard_emulate;
   if (!sharded) {
     ACE_TRY(c.enqueue_build_sym(c.A.p, 1, nullptr, 0));
   } else {
     // every rank builds its two column blocks, then the blocks are exchanged over NVLink (one grouped
-    // NCCL broadcast per block); the factorisation below is done redundantly on every rank
-    NcclApi& nc = nccl_api();
+    // NCCL broadcast per block)
     ACE_TRY(c.enqueue_build_blocks(c.A.p));
-    const int wdt = shard_block_width(c.n_pad, c.shard_world);
-    const size_t cnt = (size_t)wdt * c.n_pad;
-    ACE_NCCL(nc.GroupStart());
-    for (int blk = 0; blk < 2 * c.shard_world; ++blk) {
-      double* ptr = c.A.p + (size_t)blk * cnt;
-      ACE_NCCL(nc.Broadcast(ptr, ptr, cnt, ncclFloat64, shard_block_owner(blk, c.shard_world), f->comm, c.st));
+    if (comm) {
+      NcclApi& nc = nccl_api();
+      const int wdt = shard_block_width(c.n_pad, c.shard_world);
+      const size_t cnt = (size_t)wdt * c.n_pad;
+      ACE_NCCL(nc.GroupStart());
+      for (int blk = 0; blk < 2 * c.shard_world; ++blk) {
+        double* ptr = c.A.p + (size_t)blk * cnt;
+        ACE_NCCL(nc.Broadcast(ptr, ptr, cnt, ncclFloat64, shard_block_owner(blk, c.shard_world), f->comm, c.st));
+      }
+      ACE_NCCL(nc.GroupEnd());
     }
-    ACE_NCCL(nc.GroupEnd());
   }
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[1], c.st));
-  // Cholesky and triangular inverse overlap (potrf_trtri), so they are timed as one phase: ms[1] = both, ms[2] = 0
-  ACE_TRY(potrf_trtri(w));
-  if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
-  if (timed) ACE_CUDA(cudaEventRecord(c.tev[3], c.st));
-  ACE_TRY(uut_inverse(w));
-  if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));
-  ACE_TRY(c.enqueue_alpha(c.Bf.p, 1));
-  ACE_TRY(c.enqueue_grad(c.Bf.p));
-  if (sharded) {
-    // each rank took every world-th tile: sum its CTA partials, then all-reduce [P sums | K*alpha] so that
-    // every rank finalises with bit-identical inputs (parameters stay in lock-step without a broadcast)
-    partials_reduce_kernel<<<1, 1024, 0, c.st>>>(c.partials.p, c.gp.gx * c.gp.gy, c.P, c.red.p);
-    ACE_CUDA(cudaGetLastError());
-    ACE_NCCL(nccl_api().AllReduce(c.red.p, c.red.p, (size_t)c.P + c.n_pad, ncclFloat64, ncclSum, f->comm, c.st));
+  const bool sdense = sharded && c.shard_dense;
+  if (!sdense) {
+    // Cholesky and triangular inverse overlap (potrf_trtri), so they are timed as one phase: ms[1] = both, ms[2] = 0
+    ACE_TRY(potrf_trtri(w));
+    if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
+    if (timed) ACE_CUDA(cudaEventRecord(c.tev[3], c.st));
+    ACE_TRY(uut_inverse(w));
+    if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));
+    ACE_TRY(c.enqueue_alpha(c.Bf.p, 1));
+    c.kinv_partial = false;
+  } else {
+    // redundant Cholesky (ms[1]), then the split triangular inverse (ms[2]) and this rank's tiles of U U^T (ms[3])
+    const ShardCtx cx = c.shard_ctx(f->comm);
+    const int s = potrf_blocked(w);
+    if (s < 0) return s;
+    if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
+    ACE_TRY(trtri_merge_sharded(w, cx));
+    if (timed) ACE_CUDA(cudaEventRecord(c.tev[3], c.st));
+    ACE_TRY(uut_inverse_sharded(w, cx));
+    if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));
+    ACE_TRY(c.enqueue_alpha_tri(c.A.p, 1));
+    c.kinv_partial = !c.shard_emulate;  // an emulated run leaves the complete inverse behind
   }
-  ACE_TRY(c.enqueue_finalize(c.Bf.p, f->cfg, 1));
+  if (!sharded) {
+    ACE_TRY(c.enqueue_grad(c.Bf.p));
+  } else {
+    // each rank takes every world-th tile: sum its CTA partials, then all-reduce [P sums | K*alpha] so that
+    // every rank finalises with bit-identical inputs (parameters stay in lock-step without a broadcast)
+    for (int r = c.rank_lo(); r < c.rank_hi(); ++r) {
+      ACE_TRY(c.enqueue_grad(c.Bf.p, r, c.shard_world, sdense ? 1 : 0));
+      partials_reduce_kernel<<<1, 1024, 0, c.st>>>(c.partials.p, c.gp.gx * c.gp.gy, c.P, c.red.p, r > c.rank_lo());
+      ACE_CUDA(cudaGetLastError());
+    }
+    if (comm)
+      ACE_NCCL(nccl_api().AllReduce(c.red.p, c.red.p, (size_t)c.P + c.n_pad, ncclFloat64, ncclSum, f->comm, c.st));
+  }
+  ACE_TRY(c.enqueue_finalize(c.Bf.p, f->cfg, 1, sharded, sdense ? c.kdg.p : nullptr));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[5], c.st));
   return 0;
 }
@@ -706,6 +784,7 @@ int ace_fit_get_train_stats(ace_fit* f, double* stats) {
   if (!f || !stats) return usage("null argument");
   Core& c = f->c;
   ACE_CUDA(cudaSetDevice(c.device));
+  ACE_TRY(c.ensure_full_inverse());  // needs U, which the rebuild below overwrites
   DBuf<double> B2;  // local inverse: the stored invKmatn (c.Bf) must stay as it is (quirk Q6)
   ACE_TRY(B2.alloc((size_t)c.n_pad * c.n_pad));
   DenseWork w = c.dense(c.A.p, B2.p);
@@ -766,11 +845,33 @@ int ace_fit_shard(ace_fit* f, const char* id128, int rank, int world) {
   ncclUniqueId id;
   std::memcpy(&id, id128, 128);
   ACE_NCCL(nc.CommInitRank(&f->comm, world, id, rank));
-  ACE_TRY(c.red.alloc((size_t)c.P + c.n_pad));
-  ACE_CUDA(cudaMemsetAsync(c.red.p, 0, sizeof(double) * ((size_t)c.P + c.n_pad), c.st));
+  ACE_TRY(c.alloc_shard());
   c.shard_rank = rank;
   c.shard_world = world;
   if (f->gexec) {  // a graph captured before sharding is stale
+    cudaGraphExecDestroy(f->gexec);
+    cudaGraphDestroy(f->graph);
+    f->gexec = nullptr;
+    f->graph = nullptr;
+  }
+  f->launches = -1;
+  return 0;
+}
+
+int ace_fit_shard_emulate(ace_fit* f, int world) {
+  if (!f || world < 1) return usage("ace_fit_shard_emulate: bad argument");
+  Core& c = f->c;
+  if (world == 1) return 0;
+  ACE_CUDA(cudaSetDevice(c.device));
+  if (shard_block_width(c.n_pad, world) == 0) {
+    set_error("sharding needs ceil(n/128)*128 divisible by 128*world");
+    return ACE_ERR_UNSUPPORTED;
+  }
+  ACE_TRY(c.alloc_shard());
+  c.shard_rank = 0;
+  c.shard_world = world;
+  c.shard_emulate = true;
+  if (f->gexec) {
     cudaGraphExecDestroy(f->gexec);
     cudaGraphDestroy(f->graph);
     f->gexec = nullptr;
@@ -884,6 +985,7 @@ int ace_fit_get_optimizer_state(ace_fit* f, double* m, double* v) {
 int ace_fit_get_invKmatn(ace_fit* f, double* inv) {
   if (!f || !inv) return usage("null argument");
   ACE_CUDA(cudaSetDevice(f->c.device));
+  ACE_TRY(f->c.ensure_full_inverse());
   ACE_TRY(download_matrix(inv, f->c.n, f->c.n, f->c.Bf.p, f->c.n_pad, f->c.st));
   ACE_CUDA(cudaStreamSynchronize(f->c.st));
   return 0;
@@ -980,6 +1082,7 @@ int ace_fit_predict(ace_fit* f, const double* X2, const double* Z2, int nx, doub
   ACE_CUDA(cudaMemcpyAsync(hpar, c.theta.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c.st));
   ACE_CUDA(cudaStreamSynchronize(c.st));
   PostOut o;
+  ACE_TRY(c.ensure_full_inverse());
   ACE_TRY(posterior_rows(c, c.Bf.p, Kx.p, kd.p, nx, nx_pad, hpar[1], std::exp(hpar[0]), o));
   std::vector<double> hm(nx), hv(nx);
   ACE_CUDA(cudaMemcpyAsync(hm.data(), o.map.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));

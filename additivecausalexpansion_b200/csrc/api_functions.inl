@@ -364,6 +364,7 @@ int ace_fit_predict_marginal(ace_fit* f, const double* X2, const double* Z2, con
   double hpar[2];
   ACE_CUDA(cudaMemcpyAsync(hpar, c.theta.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c.st));
   ACE_TRY(sync_stream(c.st));
+  ACE_TRY(c.ensure_full_inverse());
   return marginal_tail(c, c.Bf.p, Kx.p, Cm.p, zx.p, nx, nx_pad, hpar[1], std_y, std_Z, calculate_ate, Z2, map, ci,
                        var, avg);
 }

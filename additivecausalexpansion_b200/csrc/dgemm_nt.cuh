@@ -41,6 +41,13 @@ struct GemmNT {
   int b_tri;            // 2: B lower triangular on the 128-block grid (k ends with the column's block)
   int lower_only;       // 1: C is square, only tiles that intersect i >= j are computed (SYRK)
   double alpha, beta;
+  // multi-GPU sharding of ONE product: this launch computes the tiles L = tile_first + q * tile_stride of the
+  // linear tile order (tile_stride 0 or 1: all tiles), so G ranks with tile_first = rank cover the output
+  // exactly once with a balanced share of the triangular k-ranges
+  int tile_first, tile_stride;
+  // A is a row slice starting at row a_row_off (multiple of 128) of the triangular operand: the k trimming and
+  // the diagonal-tile redirect use the row block index ti + a_row_off/128 (Adiag stays the unshifted tile array)
+  int a_row_off;
   // strided batch (blockIdx.y): problem q uses every pointer advanced by q * its stride (elements)
   int batch;            // 0 or 1: single problem
   long sA, sB, sC, sCt, sAdiag, sBdiag;
@@ -79,7 +86,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
   // ---- tile decode -------------------------------------------------------------------------
   int ti, tj;
   {
-    const long L = blockIdx.x;
+    const long L = (p.tile_stride > 1) ? (long)blockIdx.x * p.tile_stride + p.tile_first : (long)blockIdx.x;
     if (p.lower_only) {
       // row ti holds tiles tj = 0 .. 2*ti+1 ; rows before it hold ti*(ti+1) tiles
       long t = (long)((sqrt(4.0 * (double)L + 1.0) - 1.0) * 0.5);
@@ -100,8 +107,9 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
   }
   const int i0 = ti * BM, j0 = tj * BN;
   int k_begin = 0, k_end = p.K;
-  if (p.a_tri == 1) k_begin = i0;
-  if (p.a_tri == 2) k_end = i0 + BM;
+  const int tia = ti + p.a_row_off / TB;  // row block of this tile inside the (possibly sliced) A operand
+  if (p.a_tri == 1) k_begin = i0 + p.a_row_off;
+  if (p.a_tri == 2) k_end = i0 + p.a_row_off + BM;
   if (p.b_tri == 2) k_end = min(k_end, (j0 / TB + 1) * TB);
   const int nchunks = (k_end - k_begin) / BK;
 
@@ -127,8 +135,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
       const int k = k_begin + it * BK + kk;
       const int kb = k / TB;
       if (isA) {
-        const double* src = (gAdiag != nullptr && kb == ti)
-                                ? gAdiag + (size_t)ti * (TB * TB) + (size_t)(k % TB) * TB
+        const double* src = (gAdiag != nullptr && kb == tia)
+                                ? gAdiag + (size_t)tia * (TB * TB) + (size_t)(k % TB) * TB
                                 : gA + i0 + (size_t)k * p.lda;
         tma_bulk_g2s(As + s * A_STAGE + kk * LDAS, src, BM * 8, &full[s]);
       } else {
@@ -230,6 +238,18 @@ inline int launch_gemm_nt(const GemmNT& p, cudaStream_t stream) {
     tiles = T * (T + 1);
   } else {
     tiles = (long)(p.M / BM) * (p.N / BN);
+  }
+  if (p.tile_stride > 1) {
+    if (p.tile_first < 0 || p.tile_first >= p.tile_stride || p.batch > 1) {
+      set_error("launch_gemm_nt: bad tile subset");
+      return -2;
+    }
+    tiles = (tiles - p.tile_first + p.tile_stride - 1) / p.tile_stride;
+    if (tiles <= 0) return 0;
+  }
+  if (p.a_row_off % TB) {
+    set_error("launch_gemm_nt: a_row_off must be a multiple of 128");
+    return -2;
   }
   dim3 grid((unsigned)tiles, (unsigned)(p.batch > 1 ? p.batch : 1));
   dgemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p);

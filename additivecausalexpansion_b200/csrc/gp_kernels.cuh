@@ -125,17 +125,22 @@ __global__ void __launch_bounds__(1024) alpha_kernel(const double* __restrict__ 
                                                      int nchunks, int n, int n_pad, double* __restrict__ theta,
                                                      double* __restrict__ uvec, double* __restrict__ svec,
                                                      double* __restrict__ alpha, double* __restrict__ Ka,
-                                                     double* __restrict__ sc, int set_mu_first_iter) {
+                                                     double* __restrict__ sc, int set_mu_first_iter,
+                                                     const double* __restrict__ pd = nullptr,
+                                                     double* __restrict__ kdiag = nullptr) {
   __shared__ double red[32];
   double su = 0.0, ss = 0.0;
   for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-    double u = 0.0, s = 0.0;
+    double u = 0.0, s = 0.0, d = 0.0;
     if (i < n) {
       for (int c = 0; c < nchunks; ++c) {
         u += pu[(size_t)c * n_pad + i];
         s += ps[(size_t)c * n_pad + i];
       }
+      if (pd != nullptr)
+        for (int c = 0; c < nchunks; ++c) d += pd[(size_t)c * n_pad + i];
     }
+    if (kdiag != nullptr) kdiag[i] = d;
     uvec[i] = u;
     svec[i] = s;
     su += u;
@@ -166,6 +171,7 @@ struct FinalizeArgs {
   const double* partials;
   int nparts;
   const double *y, *alpha, *Ka, *dvec, *Kinv;
+  const double* kdiag;  // optional: diag(K^-1) as a vector (sharded inverse: no rank holds all diagonal tiles)
   long ld;
   const double* tab;
   double *theta, *m, *v, *grad, *sc;
@@ -188,7 +194,7 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const FinalizeArgs a) {
     const double r = (a.y[i] - mu) - a.Ka[i];
     s_res = fma(r, r, s_res);
     s_logd += log(a.dvec[i]);
-    s_trw += a.Kinv[i + (size_t)i * a.ld] - al * al;
+    s_trw += ((a.kdiag != nullptr) ? a.kdiag[i] : a.Kinv[i + (size_t)i * a.ld]) - al * al;
   }
   s_alpha = block_sum_1024(s_alpha, red);
   s_ya = block_sum_1024(s_ya, red);
@@ -274,12 +280,98 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const FinalizeArgs a) {
 
 // multi-GPU: sum this rank's per-CTA partial rows into red[0..P) ahead of the all-reduce
 __global__ void __launch_bounds__(1024) partials_reduce_kernel(const double* __restrict__ partials, int nparts, int P,
-                                                               double* __restrict__ red) {
+                                                               double* __restrict__ red, int accumulate = 0) {
   for (int k = threadIdx.x; k < P; k += blockDim.x) {
-    double s = 0.0;
+    double s = accumulate ? red[k] : 0.0;
     for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * P + k];
     red[k] = s;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded inverse: K^-1 = U U^T exists only tile-wise across the ranks, but every rank holds U (upper(A),
+// diagonal 128-blocks in the DU tiles).  u = K^-1 y and s = K^-1 1 are two triangular matrix-vector products
+// with U, diag(K^-1)_i = sum_k U(i,k)^2 comes with the second one.  HBM bound: the upper triangle is read twice.
+// ---------------------------------------------------------------------------------------------
+// t_y[k] = sum_{i<=k} U(i,k) y_i, t_1[k] = sum_{i<=k, i<n} U(i,k): one warp per column
+__global__ void __launch_bounds__(256) utv2_kernel(const double* __restrict__ A, long ld, const double* __restrict__ DU,
+                                                   int n, int n_pad, const double* __restrict__ y,
+                                                   double* __restrict__ ty, double* __restrict__ t1) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * 8 + warp;
+  if (k >= n_pad) return;
+  const int kb = k >> 7, kl = k & 127;
+  double sy = 0.0, s1 = 0.0;
+  const double* col = A + (size_t)k * ld;
+  const int top = min(kb * 128, n);
+  for (int i = lane; i < top; i += 32) {
+    const double u = col[i];
+    sy = fma(u, y[i], sy);
+    s1 += u;
+  }
+  const double* dcol = DU + (size_t)kb * 16384 + (size_t)kl * 128;
+  for (int il = lane; il <= kl; il += 32) {
+    const int i = kb * 128 + il;
+    if (i < n) {
+      const double u = dcol[il];
+      sy = fma(u, y[i], sy);
+      s1 += u;
+    }
+  }
+  sy = warp_sum(sy);
+  s1 = warp_sum(s1);
+  if (lane == 0) {
+    ty[k] = sy;
+    t1[k] = s1;
+  }
+}
+
+// partial sums over the column chunk blockIdx.y of u_i = sum_{k>=i} U(i,k) t_y[k], s_i (with t_1), d_i = sum U(i,k)^2
+__global__ void __launch_bounds__(gv::ROWS) uv2_kernel(const double* __restrict__ A, long ld,
+                                                       const double* __restrict__ DU, int n_pad,
+                                                       const double* __restrict__ ty, const double* __restrict__ t1,
+                                                       double* __restrict__ pu, double* __restrict__ ps,
+                                                       double* __restrict__ pd) {
+  using namespace gv;
+  __shared__ double tys[CHUNK], t1s[CHUNK];
+  const int i = blockIdx.x * ROWS + threadIdx.x;
+  const int c0 = blockIdx.y * CHUNK;
+  const int cend = min(CHUNK, n_pad - c0);
+  for (int t = threadIdx.x; t < CHUNK; t += ROWS) {
+    tys[t] = (t < cend) ? ty[c0 + t] : 0.0;
+    t1s[t] = (t < cend) ? t1[c0 + t] : 0.0;
+  }
+  __syncthreads();
+  if (i >= n_pad) return;
+  double u = 0.0, s = 0.0, d = 0.0;
+  const int rb = i >> 7, il = i & 127;
+  for (int t0 = 0; t0 < cend; t0 += 128) {
+    const int cb = (c0 + t0) >> 7;
+    if (cb < rb) continue;  // below the diagonal: zero
+    const double* src;
+    size_t stride;
+    if (cb == rb) {
+      src = DU + (size_t)rb * 16384 + il;
+      stride = 128;
+    } else {
+      src = A + i + (size_t)(c0 + t0) * ld;
+      stride = (size_t)ld;
+    }
+    for (int t = 0; t < 128; t += 8) {
+      double k[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) k[e] = src[(size_t)(t + e) * stride];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        u = fma(k[e], tys[t0 + t + e], u);
+        s = fma(k[e], t1s[t0 + t + e], s);
+        d = fma(k[e], k[e], d);
+      }
+    }
+  }
+  pu[(size_t)blockIdx.y * n_pad + i] = u;
+  ps[(size_t)blockIdx.y * n_pad + i] = s;
+  pd[(size_t)blockIdx.y * n_pad + i] = d;
 }
 
 // statistics only (stats_cpp, src/stats_cpp.cpp:9-32): needs alpha = Kinv (y - mu) and K alpha

@@ -81,14 +81,11 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
 #pragma unroll
   for (int b = 0; b < BD8; ++b) Sb[b] = 0.0;
 
-  const long ntiles = (long)a.ntiles_side * (a.ntiles_side + 1) / 2;
-  const long tstride = (long)gridDim.x * a.tile_world;
+  const long nwork = grad_work_items(a);
   uint32_t phase = 0;
-  for (long L = (long)blockIdx.x * a.tile_world + a.tile_rank; L < ntiles; L += tstride) {
-    long tt = (long)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
-    while (tt * (tt + 1) / 2 > L) --tt;
-    while ((tt + 1) * (tt + 2) / 2 <= L) ++tt;
-    const int ti = (int)tt, tj = (int)(L - tt * (tt + 1) / 2);
+  for (long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    int ti, tj;
+    if (!grad_work_tile(a, wk, ti, tj)) continue;  // uniform over the CTA
     const int i0 = ti * T, j0 = tj * T;
     const bool diag_tile = (ti == tj);
     const double wt = diag_tile ? 1.0 : 2.0;

@@ -16,6 +16,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -40,10 +41,11 @@ inline NcclApi& nccl_api() {
   api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
   api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
   api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
   api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
   api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Broadcast &&
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Broadcast && api.AllGather &&
            api.GroupStart && api.GroupEnd && api.GetErrorString;
   if (!api.ok) api.why = "libnccl.so.2 lacks a required symbol";
   return api;

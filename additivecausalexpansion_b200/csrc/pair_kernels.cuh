@@ -265,7 +265,39 @@ struct GradArgs {
   int n, p, B, P;
   int ntiles_side;   // ceil(n / 64)
   int tile_rank, tile_world;  // multi-GPU: this rank takes tiles L = tile_rank (mod tile_world); 0, 1 otherwise
+  // tile_mode 1 (sharded inverse): ownership follows the 128 x 64 tiles of the sharded U U^T launch
+  // (dgemm_nt lower_only order over gemm_rows = n_pad / 128 tile rows, tile L owned by rank L mod world), so
+  // that a rank only reads the entries of K^-1 it has computed itself; each such tile holds two 64 x 64 tiles
+  int tile_mode, gemm_rows;
 };
+
+// work item w of this launch -> lower 64 x 64 tile (ti, tj); false: nothing to do for this item
+__device__ __forceinline__ long grad_work_items(const GradArgs& a) {
+  if (a.tile_mode == 0) {
+    const long ntiles = (long)a.ntiles_side * (a.ntiles_side + 1) / 2;
+    return (ntiles - a.tile_rank + a.tile_world - 1) / a.tile_world;
+  }
+  const long ng = (long)a.gemm_rows * (a.gemm_rows + 1);
+  return 2 * ((ng - a.tile_rank + a.tile_world - 1) / a.tile_world);
+}
+__device__ __forceinline__ bool grad_work_tile(const GradArgs& a, long w, int& ti, int& tj) {
+  if (a.tile_mode == 0) {
+    const long L = w * a.tile_world + a.tile_rank;
+    long tt = (long)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
+    while (tt * (tt + 1) / 2 > L) --tt;
+    while ((tt + 1) * (tt + 2) / 2 <= L) ++tt;
+    ti = (int)tt;
+    tj = (int)(L - tt * (tt + 1) / 2);
+    return true;
+  }
+  const long L = (w >> 1) * a.tile_world + a.tile_rank;
+  long t = (long)((sqrt(4.0 * (double)L + 1.0) - 1.0) * 0.5);
+  while (t * (t + 1) > L) --t;
+  while ((t + 1) * (t + 2) <= L) ++t;
+  ti = 2 * (int)t + (int)(w & 1);
+  tj = (int)(L - t * (t + 1));
+  return tj <= ti && ti < a.ntiles_side;
+}
 
 namespace gk {
 constexpr int T = 64;
@@ -337,14 +369,11 @@ __global__ void __launch_bounds__(256, 1) grad_kernel(const GradArgs a) {
   for (int t = 0; t < BT; ++t) Sb[t] = 0.0;
 
   const double* w_mine = wgrp + gl * PD * WP;
-  const long ntiles = (long)a.ntiles_side * (a.ntiles_side + 1) / 2;
+  const long nwork = grad_work_items(a);
   uint32_t phase = 0;
-  const long tstride = (long)gridDim.x * a.tile_world;
-  for (long L = (long)blockIdx.x * a.tile_world + a.tile_rank; L < ntiles; L += tstride) {
-    long tt = (long)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
-    while (tt * (tt + 1) / 2 > L) --tt;
-    while ((tt + 1) * (tt + 2) / 2 <= L) ++tt;
-    const int ti = (int)tt, tj = (int)(L - tt * (tt + 1) / 2);
+  for (long wk = blockIdx.x; wk < nwork; wk += gridDim.x) {
+    int ti, tj;
+    if (!grad_work_tile(a, wk, ti, tj)) continue;  // uniform over the CTA
     const int i0 = ti * T, j0 = tj * T;
     const bool diag_tile = (ti == tj);
     const double wt = diag_tile ? 1.0 : 2.0;

@@ -102,6 +102,11 @@ class AceFit:
         dist.broadcast_object_list(box, src=0)
         check(lib().ace_fit_shard(self._h, box[0], rank, world), "ace_fit_shard")
 
+    def shard_emulate(self, world):
+        """Single-process stand-in for a `world`-rank sharded fit (ace_fit_shard_emulate): this process plays
+        every rank in turn on its one GPU, without NCCL; numerically the multi-GPU path."""
+        check(lib().ace_fit_shard_emulate(self._h, int(world)), "ace_fit_shard_emulate")
+
     def upload_data(self, y=None, X=None, Z=None):
         """Host -> device copy of the training data (what the per-call y, X, Z arguments of
         Kernel$para_update amount to)."""

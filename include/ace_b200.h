@@ -161,6 +161,9 @@ int ace_fit_get_train_stats(ace_fit* fit, double* stats);
 int ace_comm_unique_id(char* id128);
 int ace_shard_plan(int n, int world, int rank, int* blocks2, int* width);
 int ace_fit_shard(ace_fit* fit, const char* id128, int rank, int world);
+/* Single-process stand-in for a `world`-rank sharded fit: this process plays every rank in turn on its one GPU (no
+ * NCCL); numerically identical to the multi-GPU path, used by the single-GPU parity tests. */
+int ace_fit_shard_emulate(ace_fit* fit, int world);
 
 /* Re-upload the training data of an existing handle (same n, p, Bz): what passing y, X, Z to
  * Kernel$para_update on every call amounts to (R/kernel_SE_R6.R:40).  Any of the three may be NULL. */
