@@ -290,11 +290,14 @@ struct Core {
   int shard_hmin = 16;
   bool kinv_partial = false;   // Bf holds only this rank's tiles of K^-1 (U is complete in A)
   DBuf<double> tvy, tv1, pdg, kdg;
+  bool shard_potrf = false;    // panel-cyclic Cholesky with panel broadcasts (ACE_SHARD_POTRF=0: redundant potrf)
+  std::vector<cudaEvent_t> shard_events;
   int rank_lo() const { return shard_emulate ? 0 : shard_rank; }
   int rank_hi() const { return shard_emulate ? shard_world : shard_rank + 1; }
   ShardCtx shard_ctx(ncclComm_t comm) const {
     ShardCtx cx;
     cx.rank = shard_rank; cx.world = shard_world; cx.emulate = shard_emulate; cx.comm = comm; cx.h_min = shard_hmin;
+    cx.events = const_cast<cudaEvent_t*>(shard_events.data());
     return cx;
   }
   int alloc_shard() {
@@ -308,6 +311,23 @@ struct Core {
       ACE_TRY(tv1.alloc(n_pad));
       ACE_TRY(pdg.alloc((size_t)n_pad * nchunks));
       ACE_TRY(kdg.alloc(n_pad));
+      const char* sp = std::getenv("ACE_SHARD_POTRF");
+      const bool pow2 = (panel_blocks & (panel_blocks - 1)) == 0;
+      if ((sp ? std::atoi(sp) != 0 : true) && pow2 && panel_blocks >= 2) {
+        const size_t N = (size_t)n_pad;
+        if (!Wp0.p) {  // packed panel buffers (the fused-TRSM workspaces of the single-GPU path, if it has them)
+          ACE_TRY(Wp0.alloc(N * panel_blocks * TB));
+          ACE_TRY(Wp1.alloc(N * panel_blocks * TB));
+          ACE_TRY(Wsmall.alloc((size_t)(panel_blocks * TB / 2) * (panel_blocks * TB / 2)));
+        }
+        const int NP = shard_panels(n_pad / TB, panel_blocks);
+        while ((int)shard_events.size() < 4 * NP) {
+          cudaEvent_t e;
+          ACE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          shard_events.push_back(e);
+        }
+        shard_potrf = true;
+      }
     }
     return 0;
   }
@@ -326,6 +346,7 @@ struct Core {
       if (e) cudaEventDestroy(e);
     for (auto& e : tev)
       if (e) cudaEventDestroy(e);
+    for (auto& e : shard_events) cudaEventDestroy(e);
     if (st) cudaStreamDestroy(st);
     if (side) cudaStreamDestroy(side);
     if (aux) cudaStreamDestroy(aux);
@@ -471,6 +492,24 @@ struct Core {
     return 0;
   }
 
+  // Multi-GPU with the panel-cyclic Cholesky: the column panels this rank owns (rows >= first column of the panel)
+  int enqueue_build_panels(double* out) {
+    const int nb = n_pad / TB, NP = shard_panels(nb, panel_blocks);
+    for (int c = 0; c < NP; ++c) {
+      if (!(shard_emulate || c % shard_world == shard_rank)) continue;
+      const int c0 = c * panel_blocks * TB, w = std::min(panel_blocks * TB, n_pad - c0), r0 = c0;
+      KernArgs a{};
+      a.X1 = X.p + r0; a.Z1 = Z.p + r0; a.LZ1 = LZ.p + r0; a.ld1 = n_pad;
+      a.X2 = X.p + c0; a.Z2 = Z.p + c0; a.LZ2 = LZ.p + c0; a.ld2 = n_pad;
+      a.n1 = std::max(0, n - r0); a.n2 = std::max(0, std::min(w, n - c0));
+      a.n1_pad = n_pad - r0; a.n2_pad = w; a.p = p; a.B = B; a.tab = tab.p;
+      a.K = out + r0 + (size_t)c0 * n_pad; a.ldk = n_pad;
+      a.sym = 0; a.add_noise = 1; a.pad_identity = 1; a.row_off = r0; a.col_off = c0;
+      ACE_TRY(launch_kernmat(a, kind, st));
+    }
+    return 0;
+  }
+
   // u = Kinv y, s = Kinv 1, alpha = u - mu s (mu closed form first when asked and iter == 1)
   int enqueue_alpha(const double* Kinv, int set_mu_first_iter) {
     dim3 grid((n_pad + gv::ROWS - 1) / gv::ROWS, nchunks);
@@ -566,8 +605,12 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
   ACE_TRY(c.enqueue_prep());
   const bool sharded = c.shard_world > 1;
   const bool comm = sharded && !c.shard_emulate;
+  const bool spotrf = sharded && c.shard_dense && c.shard_potrf;
   if (!sharded) {
     ACE_TRY(c.enqueue_build_sym(c.A.p, 1, nullptr, 0));
+  } else if (spotrf) {
+    // panel-cyclic Cholesky: a rank only ever needs the K columns of the panels it owns -- no exchange
+    ACE_TRY(c.enqueue_build_panels(c.A.p));
   } else {
     // every rank builds its two column blocks, then the blocks are exchanged over NVLink (one grouped
     // NCCL broadcast per block)
@@ -598,8 +641,12 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
   } else {
     // redundant Cholesky (ms[1]), then the split triangular inverse (ms[2]) and this rank's tiles of U U^T (ms[3])
     const ShardCtx cx = c.shard_ctx(f->comm);
-    const int s = potrf_blocked(w);
-    if (s < 0) return s;
+    if (spotrf) {
+      ACE_TRY(potrf_sharded(w, cx));
+    } else {
+      const int s = potrf_blocked(w);
+      if (s < 0) return s;
+    }
     if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
     ACE_TRY(trtri_merge_sharded(w, cx));
     if (timed) ACE_CUDA(cudaEventRecord(c.tev[3], c.st));

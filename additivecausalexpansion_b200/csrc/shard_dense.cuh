@@ -12,6 +12,14 @@
 //    L mod G).  No exchange follows: the gradient pass uses exactly the same ownership (GradArgs.tile_mode 1),
 //    alpha = U (U^T ybar) and diag(K^-1) come from triangular matrix-vector products with the replicated U.
 //
+//  * Cholesky (potrf_sharded): right-looking over 512-wide column panels dealt cyclically (panel J to rank
+//    J mod G).  The owner factors the diagonal block, inverts it and solves the rows below with one triangular
+//    GEMM into a PACKED buffer ((n - j0) x 512, contiguous), which goes to everybody with one grouped
+//    ncclBroadcast (panel + DX/DU tiles + diagonal); every rank applies the panel to the panels it owns, the
+//    owner of panel J+1 first and on the high-priority stream (look-ahead), and copies it into its own A off the
+//    critical path, so that all ranks end up with the complete L.  No rank ever needs K columns it does not own:
+//    the kernel build is sharded the same way and its exchange disappears.
+//
 // `emulate`: a single process plays all G ranks one after the other on one GPU (no NCCL).  Numerically this is
 // the multi-GPU path bit for bit, which lets the single-GPU test tier cover it.
 #pragma once
@@ -25,7 +33,111 @@ struct ShardCtx {
   bool emulate = false;
   ncclComm_t comm = nullptr;
   int h_min = 16;  // levels with child size h >= h_min (in 128-blocks) and h % (2*world) == 0 are split
+  cudaEvent_t* events = nullptr;  // 4 * panels events of potrf_sharded (panel, first, step, copy)
+  int* info_tmp = nullptr;
+  bool mine(int panel) const { return emulate || panel % world == rank; }
 };
+
+inline int shard_panels(int nb, int pb) { return (nb + pb - 1) / pb; }
+
+// Phase 1 for a sharded fit.  Needs w.Wp[0..1] (packed panels) and w.Wsmall.
+inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
+  const int nb = w.nb, pb = w.panel_blocks, NP = shard_panels(nb, pb);
+  if (!w.Wp[0] || !cx.events) {
+    set_error("potrf_sharded: packed panel buffers missing");
+    return -2;
+  }
+  cudaEvent_t* ev_panel = cx.events;
+  cudaEvent_t* ev_first = cx.events + NP;
+  cudaEvent_t* ev_step = cx.events + 2 * NP;
+  cudaEvent_t* ev_copy = cx.events + 3 * NP;
+  NcclApi& nc = nccl_api();
+  ACE_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int), w.main));
+  ACE_CUDA(cudaEventRecord(w.ev_upd[1], w.main));  // fork: side and aux join after everything queued on main
+  ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_upd[1], 0));
+  ACE_CUDA(cudaStreamWaitEvent(w.aux, w.ev_upd[1], 0));
+  // panel J applied to panel c (both in panel units): A[c0:, c] -= L[c0:, J] * L[c rows, J]^T, operands packed
+  auto apply = [&](int J, int c, cudaStream_t st) -> int {
+    const int j0 = J * pb, c0 = c * pb, c1 = std::min(c0 + pb, nb);
+    const long mJ = (long)(nb - j0) * TB;
+    const double* pan = w.Wp[J & 1] + (size_t)(c0 - j0) * TB;
+    GemmNT g{};
+    g.A = pan; g.lda = mJ; g.B = pan; g.ldb = mJ; g.C = blkptr(w, c0, c0); g.ldc = w.ld;
+    g.M = (nb - c0) * TB; g.N = (c1 - c0) * TB; g.K = (std::min(j0 + pb, nb) - j0) * TB;
+    g.alpha = -1.0; g.beta = 1.0;
+    return launch_gemm_nt(g, st);
+  };
+  for (int J = 0; J < NP; ++J) {
+    const int j0 = J * pb, j1 = std::min(j0 + pb, nb);
+    const long mJ = (long)(nb - j0) * TB, wJ = (long)(j1 - j0) * TB;
+    double* Wp = w.Wp[J & 1];
+    // ---- side stream: panel J becomes available in Wp[J & 1]
+    if (J >= 2) {  // the buffer is free once panel J-2 has been applied everywhere and copied out
+      ACE_CUDA(cudaStreamWaitEvent(w.side, ev_step[J - 2], 0));
+      ACE_CUDA(cudaStreamWaitEvent(w.side, ev_copy[J - 2], 0));
+    }
+    if (cx.mine(J)) {
+      ACE_TRY(potrf_rec(w, j0, j1, w.side));
+      ACE_TRY(trtri_merge_range(w, j0, j1, w.side, w.Wsmall));  // X_JJ / U_JJ in place (early low merge levels)
+      ACE_CUDA(cudaMemcpy2DAsync(Wp, sizeof(double) * mJ, blkptr(w, j0, j0), sizeof(double) * w.ld,
+                                 sizeof(double) * wJ, (size_t)wJ, cudaMemcpyDeviceToDevice, w.side));
+      if (j1 < nb) {
+        GemmNT t{};
+        t.A = blkptr(w, j1, j0); t.lda = w.ld;
+        t.B = blkptr(w, j0, j0); t.ldb = w.ld; t.b_tri = 2; t.Bdiag = w.DX + (size_t)j0 * TB * TB;
+        t.C = Wp + wJ; t.ldc = mJ;
+        t.M = (nb - j1) * TB; t.N = (int)wJ; t.K = (int)wJ; t.alpha = 1.0; t.beta = 0.0;
+        ACE_TRY(launch_gemm_nt(t, w.side));
+      }
+    }
+    if (!cx.emulate) {
+      const int root = J % cx.world;
+      double* dx = w.DX + (size_t)j0 * TB * TB;
+      double* du = w.DU + (size_t)j0 * TB * TB;
+      double* dv = w.dvec + (size_t)j0 * TB;
+      ACE_NCCL(nc.GroupStart());
+      ACE_NCCL(nc.Broadcast(Wp, Wp, (size_t)mJ * wJ, ncclFloat64, root, cx.comm, w.side));
+      ACE_NCCL(nc.Broadcast(dx, dx, (size_t)wJ * TB, ncclFloat64, root, cx.comm, w.side));
+      ACE_NCCL(nc.Broadcast(du, du, (size_t)wJ * TB, ncclFloat64, root, cx.comm, w.side));
+      ACE_NCCL(nc.Broadcast(dv, dv, (size_t)wJ, ncclFloat64, root, cx.comm, w.side));
+      ACE_NCCL(nc.GroupEnd());
+    }
+    ACE_CUDA(cudaEventRecord(ev_panel[J], w.side));
+    // ---- aux stream: the panel into this rank's A (the owner only lacks the solved rows below the diagonal block)
+    ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_panel[J], 0));
+    {
+      const long skip = cx.mine(J) ? wJ : 0;
+      if (mJ > skip)
+        ACE_CUDA(cudaMemcpy2DAsync(blkptr(w, j0, j0) + skip, sizeof(double) * w.ld, Wp + skip, sizeof(double) * mJ,
+                                   sizeof(double) * (mJ - skip), (size_t)wJ, cudaMemcpyDeviceToDevice, w.aux));
+    }
+    ACE_CUDA(cudaEventRecord(ev_copy[J], w.aux));
+    // ---- look-ahead: the next panel, if it is mine, gets panel J at once and on the high-priority stream
+    const bool la = (J + 1 < NP) && cx.mine(J + 1);
+    if (la) {
+      if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(w.side, ev_first[J - 1], 0));  // panels <= J-1 already applied to it
+      ACE_TRY(apply(J, J + 1, w.side));
+    }
+    // ---- main stream: panel J applied to the rest of my panels, the soonest needed first
+    ACE_CUDA(cudaStreamWaitEvent(w.main, ev_panel[J], 0));
+    bool first = true;
+    for (int c = J + 1; c < NP; ++c) {
+      if (!cx.mine(c) || (la && c == J + 1)) continue;
+      ACE_TRY(apply(J, c, w.main));
+      if (first) {
+        ACE_CUDA(cudaEventRecord(ev_first[J], w.main));
+        first = false;
+      }
+    }
+    if (first) ACE_CUDA(cudaEventRecord(ev_first[J], w.main));
+    ACE_CUDA(cudaEventRecord(ev_step[J], w.main));
+  }
+  ACE_CUDA(cudaStreamWaitEvent(w.main, ev_panel[NP - 1], 0));
+  ACE_CUDA(cudaStreamWaitEvent(w.main, ev_copy[NP - 1], 0));
+  if (!cx.emulate)  // a failed pivot anywhere is everybody's failure
+    ACE_NCCL(nc.AllReduce(w.info, w.info, 1, ncclInt32, ncclMax, cx.comm, w.main));
+  return 0;
+}
 
 // packed piece (R x C, ld R) -> dst (ld ldd); optionally also its transpose -> dstT (C x R, ld lddt)
 __global__ void __launch_bounds__(256) unpack_piece_kernel(const double* __restrict__ src, int R, int C,

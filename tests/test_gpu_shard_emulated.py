@@ -42,20 +42,21 @@ def _restore(old):
             os.environ[k] = v
 
 
-# (n, p, Bz, kernel, world, h_min): nb = ceil(n/128) blocks; levels with child size h >= h_min, h % (2 world) == 0 split
+# (n, p, Bz, kernel, world, h_min, panel-cyclic potrf): nb = ceil(n/128) blocks; levels with child size h >= h_min, h % (2 world) == 0 split
 CASES = [
-    (2048, 5, 3, "SE", 2, 4),         # nb 16: levels 4 and 8 split, slices of 1 and 2 blocks
-    (2500, 20, 2, "Matern32", 2, 4),  # nb 20, ragged: lone children, ragged top node (16 + 4)
-    (4000, 8, 4, "Matern32", 4, 8),   # nb 32 (n_pad 4096): world 4, levels 8 and 16
-    (3072, 3, 1, "SE", 3, 6),         # nb 24, world 3: no level has h % 6 == 0 -> redundant inverse, split U U^T
-    (1536, 4, 2, "SE", 2, 1 << 20),   # no level split at all: only the U U^T / gradient tile ownership and the trmv
+    (2048, 5, 3, "SE", 2, 4, 1),         # nb 16: levels 4 and 8 split, slices of 1 and 2 blocks
+    (2048, 5, 3, "SE", 2, 4, 0),         # the same with the redundant Cholesky
+    (2500, 20, 2, "Matern32", 2, 4, 1),  # nb 20, ragged: lone children, ragged top node (16 + 4), 5 panels
+    (4000, 8, 4, "Matern32", 4, 8, 1),   # nb 32 (n_pad 4096): world 4, levels 8 and 16
+    (3072, 3, 1, "SE", 3, 6, 0),         # nb 24, world 3: no level has h % 6 == 0 -> redundant inverse, split U U^T
+    (1536, 4, 2, "SE", 2, 1 << 20, 1),   # no level split at all: U U^T / gradient tile ownership, trmv, panel potrf
 ]
 
 
-@pytest.mark.parametrize("n,p,Bz,kernel,world,hmin", CASES)
-def test_emulated_sharded_fit_tracks_unsharded(n, p, Bz, kernel, world, hmin):
+@pytest.mark.parametrize("n,p,Bz,kernel,world,hmin,spotrf", CASES)
+def test_emulated_sharded_fit_tracks_unsharded(n, p, Bz, kernel, world, hmin, spotrf):
     y, X, Z, par = _problem(n, p, Bz, 11 + n)
-    old = _env(ACE_SHARD_HMIN=hmin, ACE_SHARD_DENSE=1)
+    old = _env(ACE_SHARD_HMIN=hmin, ACE_SHARD_DENSE=1, ACE_SHARD_POTRF=spotrf)
     try:
         with AceFit(y, X, Z, par, kernel=kernel, use_graph=False) as s, \
                 AceFit(y, X, Z, par, kernel=kernel, use_graph=False) as g:
