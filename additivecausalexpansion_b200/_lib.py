@@ -82,6 +82,7 @@ SIGNATURES = {
     "ace_shard_plan": (_i, [_i, _i, _i, _ip, _ip]),
     "ace_fit_shard": (_i, [_vp, C.c_char_p, _i, _i]),
     "ace_fit_shard_emulate": (_i, [_vp, _i]),
+    "ace_dbg_shard_trace_dump": (_i, [_i]),
     "ace_fit_upload_data": (_i, [_vp, _p, _p, _p]),
     "ace_fit_kernel_launches": (_i, [_vp, _ip]),
     "ace_fit_timer_start": (_i, [_vp]),

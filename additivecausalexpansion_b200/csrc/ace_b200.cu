@@ -292,12 +292,16 @@ struct Core {
   DBuf<double> tvy, tv1, pdg, kdg;
   bool shard_potrf = false;    // panel-cyclic Cholesky with panel broadcasts (ACE_SHARD_POTRF=0: redundant potrf)
   std::vector<cudaEvent_t> shard_events;
+  DBuf<double> head0, head1;   // packed panel heads (shard_dense.cuh)
+  cudaStream_t bulk = nullptr; // bulk panel pieces: own stream (and communicator)
   int rank_lo() const { return shard_emulate ? 0 : shard_rank; }
   int rank_hi() const { return shard_emulate ? shard_world : shard_rank + 1; }
-  ShardCtx shard_ctx(ncclComm_t comm) const {
+  ShardCtx shard_ctx(ncclComm_t comm, ncclComm_t comm2) const {
     ShardCtx cx;
     cx.rank = shard_rank; cx.world = shard_world; cx.emulate = shard_emulate; cx.comm = comm; cx.h_min = shard_hmin;
+    cx.comm2 = comm2;
     cx.events = const_cast<cudaEvent_t*>(shard_events.data());
+    cx.head[0] = head0.p; cx.head[1] = head1.p; cx.bulk_stream = bulk;
     return cx;
   }
   int alloc_shard() {
@@ -320,8 +324,16 @@ struct Core {
           ACE_TRY(Wp1.alloc(N * panel_blocks * TB));
           ACE_TRY(Wsmall.alloc((size_t)(panel_blocks * TB / 2) * (panel_blocks * TB / 2)));
         }
+        const size_t pw = (size_t)panel_blocks * TB;
+        ACE_TRY(head0.alloc(2 * pw * pw));
+        ACE_TRY(head1.alloc(2 * pw * pw));
+        if (!bulk) {
+          int lo = 0, hi = 0;
+          ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+          ACE_CUDA(cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, hi));
+        }
         const int NP = shard_panels(n_pad / TB, panel_blocks);
-        while ((int)shard_events.size() < 4 * NP) {
+        while ((int)shard_events.size() < SHARD_EVENT_KINDS * NP) {
           cudaEvent_t e;
           ACE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
           shard_events.push_back(e);
@@ -347,6 +359,7 @@ struct Core {
     for (auto& e : tev)
       if (e) cudaEventDestroy(e);
     for (auto& e : shard_events) cudaEventDestroy(e);
+    if (bulk) cudaStreamDestroy(bulk);
     if (st) cudaStreamDestroy(st);
     if (side) cudaStreamDestroy(side);
     if (aux) cudaStreamDestroy(aux);
@@ -588,8 +601,9 @@ struct ace_fit {
   cudaGraphExec_t gexec = nullptr;
   double iter_dev = 0.0;  // host shadow of sc[SC_ITER]
   double ms[6] = {0, 0, 0, 0, 0, 0};
-  ncclComm_t comm = nullptr;  // multi-GPU sharded mode
+  ncclComm_t comm = nullptr, comm2 = nullptr;  // multi-GPU sharded mode
   ~ace_fit() {
+    if (comm2 && nccl_api().ok) nccl_api().CommDestroy(comm2);
     if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
     if (sw0) cudaEventDestroy(sw0);
     if (sw1) cudaEventDestroy(sw1);
@@ -640,7 +654,7 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
     c.kinv_partial = false;
   } else {
     // redundant Cholesky (ms[1]), then the split triangular inverse (ms[2]) and this rank's tiles of U U^T (ms[3])
-    const ShardCtx cx = c.shard_ctx(f->comm);
+    const ShardCtx cx = c.shard_ctx(f->comm, f->comm2);
     if (spotrf) {
       ACE_TRY(potrf_sharded(w, cx));
     } else {
@@ -892,6 +906,19 @@ int ace_fit_shard(ace_fit* f, const char* id128, int rank, int world) {
   ncclUniqueId id;
   std::memcpy(&id, id128, 128);
   ACE_NCCL(nc.CommInitRank(&f->comm, world, id, rank));
+  {  // second communicator (bulk panel broadcasts): its id is created on rank 0 and travels over the first one
+    ncclUniqueId id2;
+    DBuf<double> box;
+    ACE_TRY(box.alloc(16));
+    if (rank == 0) {
+      ACE_NCCL(nc.GetUniqueId(&id2));
+      ACE_CUDA(cudaMemcpyAsync(box.p, &id2, 128, cudaMemcpyHostToDevice, c.st));
+    }
+    ACE_NCCL(nc.Broadcast(box.p, box.p, 16, ncclFloat64, 0, f->comm, c.st));
+    ACE_CUDA(cudaMemcpyAsync(&id2, box.p, 128, cudaMemcpyDeviceToHost, c.st));
+    ACE_CUDA(cudaStreamSynchronize(c.st));
+    ACE_NCCL(nc.CommInitRank(&f->comm2, world, id2, rank));
+  }
   ACE_TRY(c.alloc_shard());
   c.shard_rank = rank;
   c.shard_world = world;
@@ -925,6 +952,11 @@ int ace_fit_shard_emulate(ace_fit* f, int world) {
     f->graph = nullptr;
   }
   f->launches = -1;
+  return 0;
+}
+
+int ace_dbg_shard_trace_dump(int rank) {
+  shard_trace_dump(rank);
   return 0;
 }
 

@@ -51,6 +51,7 @@ struct GemmNT {
   // strided batch (blockIdx.y): problem q uses every pointer advanced by q * its stride (elements)
   int batch;            // 0 or 1: single problem
   long sA, sB, sC, sCt, sAdiag, sBdiag;
+  int m_dec;            // batched problems of shrinking height: problem q has M - q * m_dec rows (tiles beyond exit)
 };
 
 namespace gemm {
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
     }
   }
   const int i0 = ti * BM, j0 = tj * BN;
+  if (i0 >= p.M - (int)q * p.m_dec) return;  // whole CTA, before any barrier exists
   int k_begin = 0, k_end = p.K;
   const int tia = ti + p.a_row_off / TB;  // row block of this tile inside the (possibly sliced) A operand
   if (p.a_tri == 1) k_begin = i0 + p.a_row_off;

@@ -23,6 +23,7 @@
 // `emulate`: a single process plays all G ranks one after the other on one GPU (no NCCL).  Numerically this is
 // the multi-GPU path bit for bit, which lets the single-GPU test tier cover it.
 #pragma once
+#include <cstdio>
 #include "chol.cuh"
 #include "nccl_dyn.h"
 
@@ -33,106 +34,225 @@ struct ShardCtx {
   bool emulate = false;
   ncclComm_t comm = nullptr;
   int h_min = 16;  // levels with child size h >= h_min (in 128-blocks) and h % (2*world) == 0 are split
-  cudaEvent_t* events = nullptr;  // 4 * panels events of potrf_sharded (panel, first, step, copy)
-  int* info_tmp = nullptr;
+  ncclComm_t comm2 = nullptr;       // second communicator: bulk panel broadcasts (never queue behind the heads)
+  cudaEvent_t* events = nullptr;    // SHARD_EVENT_KINDS * panels events of potrf_sharded
+  double* head[2] = {nullptr, nullptr};  // packed panel heads, (2 * panel width) x (panel width) doubles each
+  cudaStream_t bulk_stream = nullptr;
   bool mine(int panel) const { return emulate || panel % world == rank; }
 };
 
 inline int shard_panels(int nb, int pb) { return (nb + pb - 1) / pb; }
+constexpr int SHARD_EVENT_KINDS = 7;
 
-// Phase 1 for a sharded fit.  Needs w.Wp[0..1] (packed panels) and w.Wsmall.
+// ACE_SHARD_TRACE=1: per-panel timeline of potrf_sharded (CUDA events with timing), printed by shard_trace_dump
+struct ShardTrace {
+  cudaEvent_t t0 = nullptr;
+  std::vector<cudaEvent_t> ev;  // 9 per panel: s0 s1 s2 s3 | b1 b2 b3 | m0 m1
+  int np = 0;
+  void mark(int J, int k, cudaStream_t st) {
+    if (!t0) return;
+    cudaEventRecord(ev[(size_t)J * 9 + k], st);
+  }
+};
+inline ShardTrace& shard_trace() {
+  static ShardTrace t;
+  return t;
+}
+inline void shard_trace_begin(int NP, cudaStream_t st) {
+  ShardTrace& t = shard_trace();
+  static const bool on = std::getenv("ACE_SHARD_TRACE") != nullptr;
+  if (!on) return;
+  if (!t.t0) cudaEventCreate(&t.t0);
+  while ((int)t.ev.size() < 9 * NP) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    t.ev.push_back(e);
+  }
+  t.np = NP;
+  cudaEventRecord(t.t0, st);
+}
+inline void shard_trace_dump(int rank) {
+  ShardTrace& t = shard_trace();
+  if (!t.t0) return;
+  cudaDeviceSynchronize();
+  std::fprintf(stderr, "[shard trace rank %d] J: factor_begin head_ready head_bcast diag_applied | bulk_trsm bulk_bcast la_applied | main_begin main_end (ms)\n", rank);
+  for (int J = 0; J < t.np; ++J) {
+    float v[9];
+    for (int k = 0; k < 9; ++k)
+      if (cudaEventElapsedTime(&v[k], t.t0, t.ev[(size_t)J * 9 + k]) != cudaSuccess) v[k] = -1.f;
+    std::fprintf(stderr, "[shard trace rank %d] %2d: %7.3f %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f | %7.3f %7.3f\n", rank, J, v[0],
+                 v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+  }
+  cudaGetLastError();
+}
+
+// Phase 1 for a sharded fit.  Needs w.Wp[0..1] (packed bulk of a panel), cx.head[0..1] (packed head), w.Wsmall.
+//
+// A panel travels in two pieces so that the serial chain of the factorisation only carries what it must:
+//   head(J) = diagonal block (factor + its inverse) and the rows of the NEXT panel, L[J+1 rows, J]: all the owner
+//             of panel J+1 needs to finish and factor ITS diagonal block.  Small (<= 1024 x 512), own communicator,
+//             high-priority stream -> chain per panel = diagonal factorisation + one small GEMM + one small broadcast.
+//   bulk(J) = the rows below, needed only when the next head is solved, i.e. one diagonal factorisation later; own
+//             stream and communicator, so the two transfers never queue behind each other.
 inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
   const int nb = w.nb, pb = w.panel_blocks, NP = shard_panels(nb, pb);
-  if (!w.Wp[0] || !cx.events) {
+  if (!w.Wp[0] || !cx.events || !cx.head[0] || !cx.bulk_stream) {
     set_error("potrf_sharded: packed panel buffers missing");
     return -2;
   }
-  cudaEvent_t* ev_panel = cx.events;
-  cudaEvent_t* ev_first = cx.events + NP;
-  cudaEvent_t* ev_step = cx.events + 2 * NP;
-  cudaEvent_t* ev_copy = cx.events + 3 * NP;
+  cudaEvent_t* ev_head = cx.events;            // side : head(J) available in head[J & 1]
+  cudaEvent_t* ev_bulk = cx.events + NP;       // bulk : bulk(J) available in Wp[J & 1]
+  cudaEvent_t* ev_la = cx.events + 2 * NP;     // bulk : panel J fully applied to panel J+1 (look-ahead, rows below its diagonal block)
+  cudaEvent_t* ev_first = cx.events + 3 * NP;  // main : panel J applied to my soonest-needed panel
+  cudaEvent_t* ev_step = cx.events + 4 * NP;   // main : panel J applied to all my panels
+  cudaEvent_t* ev_copy = cx.events + 5 * NP;   // aux  : panel J copied into A
+  cudaEvent_t* ev_diag = cx.events + 6 * NP;   // side : head(J) applied to the diagonal block of panel J+1
   NcclApi& nc = nccl_api();
+  cudaStream_t bulk = cx.bulk_stream;
   ACE_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int), w.main));
-  ACE_CUDA(cudaEventRecord(w.ev_upd[1], w.main));  // fork: side and aux join after everything queued on main
+  ACE_CUDA(cudaEventRecord(w.ev_upd[1], w.main));  // fork: the other streams join after everything queued on main
   ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_upd[1], 0));
+  ACE_CUDA(cudaStreamWaitEvent(bulk, w.ev_upd[1], 0));
   ACE_CUDA(cudaStreamWaitEvent(w.aux, w.ev_upd[1], 0));
-  // panel J applied to panel c (both in panel units): A[c0:, c] -= L[c0:, J] * L[c rows, J]^T, operands packed
-  auto apply = [&](int J, int c, cudaStream_t st) -> int {
-    const int j0 = J * pb, c0 = c * pb, c1 = std::min(c0 + pb, nb);
-    const long mJ = (long)(nb - j0) * TB;
-    const double* pan = w.Wp[J & 1] + (size_t)(c0 - j0) * TB;
-    GemmNT g{};
-    g.A = pan; g.lda = mJ; g.B = pan; g.ldb = mJ; g.C = blkptr(w, c0, c0); g.ldc = w.ld;
-    g.M = (nb - c0) * TB; g.N = (c1 - c0) * TB; g.K = (std::min(j0 + pb, nb) - j0) * TB;
-    g.alpha = -1.0; g.beta = 1.0;
-    return launch_gemm_nt(g, st);
-  };
+  shard_trace_begin(NP, w.main);
+  ShardTrace& tr = shard_trace();
   for (int J = 0; J < NP; ++J) {
-    const int j0 = J * pb, j1 = std::min(j0 + pb, nb);
-    const long mJ = (long)(nb - j0) * TB, wJ = (long)(j1 - j0) * TB;
+    const int j0 = J * pb, j1 = std::min(j0 + pb, nb), j2 = std::min(j1 + pb, nb);
+    const long wJ = (long)(j1 - j0) * TB, wN = (long)(j2 - j1) * TB;  // panel width, next panel's width
+    const long hJ = wJ + wN, mB = (long)(nb - j2) * TB;               // head rows, bulk rows
+    double* Hd = cx.head[J & 1];
     double* Wp = w.Wp[J & 1];
-    // ---- side stream: panel J becomes available in Wp[J & 1]
-    if (J >= 2) {  // the buffer is free once panel J-2 has been applied everywhere and copied out
-      ACE_CUDA(cudaStreamWaitEvent(w.side, ev_step[J - 2], 0));
+    const bool mine = cx.mine(J), la = (J + 1 < NP) && cx.mine(J + 1);
+    // ================= head(J): side stream, communicator `comm`
+    if (J >= 2) {  // head buffer free: its readers were side (in order), the bulk look-ahead and the copy-out of J-2
+      ACE_CUDA(cudaStreamWaitEvent(w.side, ev_la[J - 2], 0));
       ACE_CUDA(cudaStreamWaitEvent(w.side, ev_copy[J - 2], 0));
     }
-    if (cx.mine(J)) {
+    tr.mark(J, 0, w.side);
+    if (mine) {
       ACE_TRY(potrf_rec(w, j0, j1, w.side));
       ACE_TRY(trtri_merge_range(w, j0, j1, w.side, w.Wsmall));  // X_JJ / U_JJ in place (early low merge levels)
-      ACE_CUDA(cudaMemcpy2DAsync(Wp, sizeof(double) * mJ, blkptr(w, j0, j0), sizeof(double) * w.ld,
+      ACE_CUDA(cudaMemcpy2DAsync(Hd, sizeof(double) * hJ, blkptr(w, j0, j0), sizeof(double) * w.ld,
                                  sizeof(double) * wJ, (size_t)wJ, cudaMemcpyDeviceToDevice, w.side));
-      if (j1 < nb) {
+      if (wN > 0) {
+        if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(w.side, ev_la[J - 1], 0));  // rows below my diagonal block are up to date
         GemmNT t{};
         t.A = blkptr(w, j1, j0); t.lda = w.ld;
         t.B = blkptr(w, j0, j0); t.ldb = w.ld; t.b_tri = 2; t.Bdiag = w.DX + (size_t)j0 * TB * TB;
-        t.C = Wp + wJ; t.ldc = mJ;
-        t.M = (nb - j1) * TB; t.N = (int)wJ; t.K = (int)wJ; t.alpha = 1.0; t.beta = 0.0;
+        t.C = Hd + wJ; t.ldc = hJ;
+        t.M = (int)wN; t.N = (int)wJ; t.K = (int)wJ; t.alpha = 1.0; t.beta = 0.0;
         ACE_TRY(launch_gemm_nt(t, w.side));
       }
     }
+    tr.mark(J, 1, w.side);
     if (!cx.emulate) {
       const int root = J % cx.world;
       double* dx = w.DX + (size_t)j0 * TB * TB;
       double* du = w.DU + (size_t)j0 * TB * TB;
       double* dv = w.dvec + (size_t)j0 * TB;
       ACE_NCCL(nc.GroupStart());
-      ACE_NCCL(nc.Broadcast(Wp, Wp, (size_t)mJ * wJ, ncclFloat64, root, cx.comm, w.side));
+      ACE_NCCL(nc.Broadcast(Hd, Hd, (size_t)hJ * wJ, ncclFloat64, root, cx.comm, w.side));
       ACE_NCCL(nc.Broadcast(dx, dx, (size_t)wJ * TB, ncclFloat64, root, cx.comm, w.side));
       ACE_NCCL(nc.Broadcast(du, du, (size_t)wJ * TB, ncclFloat64, root, cx.comm, w.side));
       ACE_NCCL(nc.Broadcast(dv, dv, (size_t)wJ, ncclFloat64, root, cx.comm, w.side));
       ACE_NCCL(nc.GroupEnd());
     }
-    ACE_CUDA(cudaEventRecord(ev_panel[J], w.side));
-    // ---- aux stream: the panel into this rank's A (the owner only lacks the solved rows below the diagonal block)
-    ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_panel[J], 0));
+    ACE_CUDA(cudaEventRecord(ev_head[J], w.side));
+    tr.mark(J, 2, w.side);
+    if (la) {  // diagonal block of the next panel: A[J+1, J+1] -= Hn Hn^T with Hn = L[J+1 rows, J]
+      if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(w.side, ev_first[J - 1], 0));  // panels <= J-1 already applied to it
+      GemmNT g{};
+      g.A = Hd + wJ; g.lda = hJ; g.B = Hd + wJ; g.ldb = hJ; g.C = blkptr(w, j1, j1); g.ldc = w.ld;
+      g.M = (int)wN; g.N = (int)wN; g.K = (int)wJ; g.alpha = -1.0; g.beta = 1.0;
+      ACE_TRY(launch_gemm_nt(g, w.side));
+    }
+    ACE_CUDA(cudaEventRecord(ev_diag[J], w.side));
+    tr.mark(J, 3, w.side);
+    // ================= bulk(J): rows [j2, nb), bulk stream, communicator `comm2`
+    if (J >= 2) {  // Wp[J & 1] free: readers were main (step J-2), the bulk stream itself and the copy-out
+      ACE_CUDA(cudaStreamWaitEvent(bulk, ev_step[J - 2], 0));
+      ACE_CUDA(cudaStreamWaitEvent(bulk, ev_copy[J - 2], 0));
+    }
+    ACE_CUDA(cudaStreamWaitEvent(bulk, ev_head[J], 0));  // X_JJ (owner) / head data (look-ahead apply below)
+    if (mB > 0) {
+      if (mine) {
+        GemmNT t{};
+        t.A = blkptr(w, j2, j0); t.lda = w.ld;
+        t.B = blkptr(w, j0, j0); t.ldb = w.ld; t.b_tri = 2; t.Bdiag = w.DX + (size_t)j0 * TB * TB;
+        t.C = Wp; t.ldc = mB;
+        t.M = (int)mB; t.N = (int)wJ; t.K = (int)wJ; t.alpha = 1.0; t.beta = 0.0;
+        ACE_TRY(launch_gemm_nt(t, bulk));
+      }
+      tr.mark(J, 4, bulk);
+      if (!cx.emulate) ACE_NCCL(nc.Broadcast(Wp, Wp, (size_t)mB * wJ, ncclFloat64, J % cx.world, cx.comm2, bulk));
+    } else {
+      tr.mark(J, 4, bulk);
+    }
+    ACE_CUDA(cudaEventRecord(ev_bulk[J], bulk));
+    tr.mark(J, 5, bulk);
+    if (la && mB > 0) {  // rows below the next panel's diagonal block: A[j2:, J+1] -= bulk * Hn^T
+      if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(bulk, ev_first[J - 1], 0));
+      GemmNT g{};
+      g.A = Wp; g.lda = mB; g.B = Hd + wJ; g.ldb = hJ; g.C = blkptr(w, j2, j1); g.ldc = w.ld;
+      g.M = (int)mB; g.N = (int)wN; g.K = (int)wJ; g.alpha = -1.0; g.beta = 1.0;
+      ACE_TRY(launch_gemm_nt(g, bulk));
+    }
+    ACE_CUDA(cudaEventRecord(ev_la[J], bulk));
+    tr.mark(J, 6, bulk);
+    // ================= aux stream: the panel into this rank's A (the owner already has its diagonal block)
+    ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_head[J], 0));
+    ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_bulk[J], 0));
     {
-      const long skip = cx.mine(J) ? wJ : 0;
-      if (mJ > skip)
-        ACE_CUDA(cudaMemcpy2DAsync(blkptr(w, j0, j0) + skip, sizeof(double) * w.ld, Wp + skip, sizeof(double) * mJ,
-                                   sizeof(double) * (mJ - skip), (size_t)wJ, cudaMemcpyDeviceToDevice, w.aux));
+      const long skip = mine ? wJ : 0;
+      if (hJ > skip)
+        ACE_CUDA(cudaMemcpy2DAsync(blkptr(w, j0, j0) + skip, sizeof(double) * w.ld, Hd + skip, sizeof(double) * hJ,
+                                   sizeof(double) * (hJ - skip), (size_t)wJ, cudaMemcpyDeviceToDevice, w.aux));
+      if (mB > 0)
+        ACE_CUDA(cudaMemcpy2DAsync(blkptr(w, j2, j0), sizeof(double) * w.ld, Wp, sizeof(double) * mB,
+                                   sizeof(double) * mB, (size_t)wJ, cudaMemcpyDeviceToDevice, w.aux));
     }
     ACE_CUDA(cudaEventRecord(ev_copy[J], w.aux));
-    // ---- look-ahead: the next panel, if it is mine, gets panel J at once and on the high-priority stream
-    const bool la = (J + 1 < NP) && cx.mine(J + 1);
-    if (la) {
-      if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(w.side, ev_first[J - 1], 0));  // panels <= J-1 already applied to it
-      ACE_TRY(apply(J, J + 1, w.side));
-    }
-    // ---- main stream: panel J applied to the rest of my panels, the soonest needed first
-    ACE_CUDA(cudaStreamWaitEvent(w.main, ev_panel[J], 0));
+    // ================= main stream: panel J applied to the rest of my panels (all below row j2: bulk operands)
+    ACE_CUDA(cudaStreamWaitEvent(w.main, ev_bulk[J], 0));
+    tr.mark(J, 7, w.main);
     bool first = true;
-    for (int c = J + 1; c < NP; ++c) {
-      if (!cx.mine(c) || (la && c == J + 1)) continue;
-      ACE_TRY(apply(J, c, w.main));
-      if (first) {
+    {
+      // my panels c >= J+2: the soonest needed one alone (its completion releases the look-ahead), all other
+      // full-width ones in ONE batched launch of shrinking height (one tail instead of one per panel), a ragged
+      // last panel alone
+      const int G = cx.emulate ? 1 : cx.world;
+      int cf = J + 2;
+      while (cf < NP && !cx.mine(cf)) ++cf;
+      auto apply = [&](int c, int count) -> int {
+        const int c0 = c * pb, c1 = std::min(c0 + pb, nb);
+        const double* pan = Wp + (size_t)(c0 - j2) * TB;
+        GemmNT g{};
+        g.A = pan; g.lda = mB; g.B = pan; g.ldb = mB; g.C = blkptr(w, c0, c0); g.ldc = w.ld;
+        g.M = (nb - c0) * TB; g.N = (c1 - c0) * TB; g.K = (int)wJ; g.alpha = -1.0; g.beta = 1.0;
+        if (count > 1) {
+          const long step = (long)G * pb * TB;
+          g.batch = count; g.sA = step; g.sB = step; g.sC = step * (w.ld + 1); g.m_dec = (int)step;
+        }
+        return launch_gemm_nt(g, w.main);
+      };
+      if (cf < NP) {
+        ACE_TRY(apply(cf, 1));
         ACE_CUDA(cudaEventRecord(ev_first[J], w.main));
         first = false;
+        int cnt = 0, last_ragged = -1;
+        for (int c = cf + G; c < NP; c += G) {
+          if ((c + 1) * pb > nb) last_ragged = c; else ++cnt;
+        }
+        if (cnt > 0) ACE_TRY(apply(cf + G, cnt));
+        if (last_ragged >= 0) ACE_TRY(apply(last_ragged, 1));
       }
     }
     if (first) ACE_CUDA(cudaEventRecord(ev_first[J], w.main));
     ACE_CUDA(cudaEventRecord(ev_step[J], w.main));
+    tr.mark(J, 8, w.main);
   }
-  ACE_CUDA(cudaStreamWaitEvent(w.main, ev_panel[NP - 1], 0));
+  ACE_CUDA(cudaStreamWaitEvent(w.main, ev_diag[NP - 1], 0));
+  ACE_CUDA(cudaStreamWaitEvent(w.main, ev_la[NP - 1], 0));
   ACE_CUDA(cudaStreamWaitEvent(w.main, ev_copy[NP - 1], 0));
   if (!cx.emulate)  // a failed pivot anywhere is everybody's failure
     ACE_NCCL(nc.AllReduce(w.info, w.info, 1, ncclInt32, ncclMax, cx.comm, w.main));

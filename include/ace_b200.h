@@ -164,6 +164,8 @@ int ace_fit_shard(ace_fit* fit, const char* id128, int rank, int world);
 /* Single-process stand-in for a `world`-rank sharded fit: this process plays every rank in turn on its one GPU (no
  * NCCL); numerically identical to the multi-GPU path, used by the single-GPU parity tests. */
 int ace_fit_shard_emulate(ace_fit* fit, int world);
+/* ACE_SHARD_TRACE=1: print the per-panel event timeline of the last sharded Cholesky to stderr (debug). */
+int ace_dbg_shard_trace_dump(int rank);
 
 /* Re-upload the training data of an existing handle (same n, p, Bz): what passing y, X, Z to
  * Kernel$para_update on every call amounts to (R/kernel_SE_R6.R:40).  Any of the three may be NULL. */

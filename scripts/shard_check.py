@@ -28,6 +28,9 @@ with AceFit(prob.y, prob.X, prob.Z, prob.parameters, kernel=prob.kernel, std_y=p
         f.para_update(it)
     ms_sh = f.timer_stop() / 3
     ph = f.last_timing_ms
+    if os.environ.get("ACE_SHARD_TRACE") and rank in (0, 1):
+        from additivecausalexpansion_b200._lib import lib
+        lib().ace_dbg_shard_trace_dump(rank)
 # bit-identical parameters on all ranks?
 par = torch.tensor(res[-1][2], device=f"cuda:{lr}")
 gathered = [torch.empty_like(par) for _ in range(world)]
