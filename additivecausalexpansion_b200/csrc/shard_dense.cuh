@@ -49,6 +49,16 @@ struct ShardTrace {
   cudaEvent_t t0 = nullptr;
   std::vector<cudaEvent_t> ev;  // 9 per panel: s0 s1 s2 s3 | b1 b2 b3 | m0 m1
   int np = 0;
+  std::vector<cudaEvent_t> lev;   // triangular inverse: 5 per level (begin, gemm1, gemm2, gather, unpack)
+  std::vector<int> lev_h;
+  void level_mark(int h, int k, cudaStream_t st) {
+    if (!t0) return;
+    if (k == 0) lev_h.push_back(h);
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    lev.push_back(e);
+  }
   void mark(int J, int k, cudaStream_t st) {
     if (!t0) return;
     cudaEventRecord(ev[(size_t)J * 9 + k], st);
@@ -69,6 +79,9 @@ inline void shard_trace_begin(int NP, cudaStream_t st) {
     t.ev.push_back(e);
   }
   t.np = NP;
+  for (auto e : t.lev) cudaEventDestroy(e);
+  t.lev.clear();
+  t.lev_h.clear();
   cudaEventRecord(t.t0, st);
 }
 inline void shard_trace_dump(int rank) {
@@ -82,6 +95,14 @@ inline void shard_trace_dump(int rank) {
       if (cudaEventElapsedTime(&v[k], t.t0, t.ev[(size_t)J * 9 + k]) != cudaSuccess) v[k] = -1.f;
     std::fprintf(stderr, "[shard trace rank %d] %2d: %7.3f %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f | %7.3f %7.3f\n", rank, J, v[0],
                  v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+  }
+  for (size_t l = 0; l < t.lev_h.size(); ++l) {
+    float v[5];
+    for (int k = 0; k < 5; ++k)
+      if (cudaEventElapsedTime(&v[k], t.t0, t.lev[l * 5 + k]) != cudaSuccess) v[k] = -1.f;
+    std::fprintf(stderr, "[shard trace rank %d] trtri level h=%d (%s): begin %.3f gemm1 +%.3f gemm2 +%.3f gather +%.3f unpack +%.3f\n",
+                 rank, t.lev_h[l] < 0 ? -t.lev_h[l] : t.lev_h[l], t.lev_h[l] < 0 ? "redundant" : "split", v[0], v[1] - v[0],
+                 v[2] - v[1], v[3] - v[2], v[4] - v[3]);
   }
   cudaGetLastError();
 }
@@ -307,7 +328,29 @@ inline int trtri_level_sharded(const DenseWork& w, int lo, int len, int h, cudaS
   double* wt = ws + (size_t)G * chunk;   // Wt slices of the rank(s) this process computes
   const int r_lo = cx.emulate ? 0 : cx.rank, r_hi = cx.emulate ? G : cx.rank + 1;
   auto slice_of = [&](int r, int e) { return e == 0 ? r : 2 * G - 1 - r; };
+  // The slice products of one phase are independent and individually too small to fill the GPU at the lower split
+  // levels, so they are dealt over three streams (st + the two helper streams of the dense engine) and joined.
+  cudaStream_t ss[3] = {st, w.side, w.aux};
+  const int ns = (w.side && w.aux && st == w.main) ? 3 : 1;
+  auto fork = [&]() -> int {
+    if (ns == 1) return 0;
+    ACE_CUDA(cudaEventRecord(w.ev_upd[0], st));
+    ACE_CUDA(cudaStreamWaitEvent(ss[1], w.ev_upd[0], 0));
+    ACE_CUDA(cudaStreamWaitEvent(ss[2], w.ev_upd[0], 0));
+    return 0;
+  };
+  auto join = [&]() -> int {
+    if (ns == 1) return 0;
+    ACE_CUDA(cudaEventRecord(w.ev_panel[0], ss[1]));
+    ACE_CUDA(cudaEventRecord(w.ev_panel[1], ss[2]));
+    ACE_CUDA(cudaStreamWaitEvent(st, w.ev_panel[0], 0));
+    ACE_CUDA(cudaStreamWaitEvent(st, w.ev_panel[1], 0));
+    return 0;
+  };
   // Wt[slice] = U11[slice rows, :] * L21^T    (all of them BEFORE any X21 overwrites L21)
+  shard_trace().level_mark(h, 0, st);
+  ACE_TRY(fork());
+  int li = 0;
   for (int r = r_lo; r < r_hi; ++r)
     for (const Node& nd : nodes)
       for (int e = 0; e < 2; ++e) {
@@ -318,9 +361,13 @@ inline int trtri_level_sharded(const DenseWork& w, int lo, int len, int h, cudaS
         p.B = blkptr(w, nd.c, nd.a); p.ldb = w.ld;
         p.C = wt + (size_t)(r - r_lo) * chunk + nd.off + (size_t)e * Rs * nd.s2; p.ldc = Rs;
         p.M = Rs; p.N = nd.s2; p.K = s1; p.alpha = 1.0; p.beta = 0.0;
-        ACE_TRY(launch_gemm_nt(p, st));
+        ACE_TRY(launch_gemm_nt(p, ss[li++ % ns]));
       }
+  ACE_TRY(join());
+  shard_trace().level_mark(h, 1, st);
   // X21[:, slice] = -X22 * Wt[slice]^T, transposed copy (= U12[slice rows, :]) packed into the staging chunk
+  ACE_TRY(fork());
+  li = 0;
   for (int r = r_lo; r < r_hi; ++r)
     for (const Node& nd : nodes)
       for (int e = 0; e < 2; ++e) {
@@ -331,12 +378,15 @@ inline int trtri_level_sharded(const DenseWork& w, int lo, int len, int h, cudaS
         q.C = blkptr(w, nd.c, nd.a) + (size_t)ro * w.ld; q.ldc = w.ld;
         q.Ct = stage + (size_t)r * chunk + nd.off + (size_t)e * Rs * nd.s2; q.ldct = Rs;
         q.M = nd.s2; q.N = Rs; q.K = nd.s2; q.alpha = -1.0; q.beta = 0.0;
-        ACE_TRY(launch_gemm_nt(q, st));
+        ACE_TRY(launch_gemm_nt(q, ss[li++ % ns]));
       }
+  ACE_TRY(join());
+  shard_trace().level_mark(h, 2, st);
   if (!cx.emulate) {
     NcclApi& nc = nccl_api();
     ACE_NCCL(nc.AllGather(stage + (size_t)cx.rank * chunk, stage, chunk, ncclFloat64, cx.comm, st));
   }
+  shard_trace().level_mark(h, 3, st);
   for (int r = 0; r < G; ++r)
     for (const Node& nd : nodes)
       for (int e = 0; e < 2; ++e) {
@@ -347,6 +397,7 @@ inline int trtri_level_sharded(const DenseWork& w, int lo, int len, int h, cudaS
                                                   need_lower ? blkptr(w, nd.c, nd.a + sl * hs) : nullptr, w.ld);
         ACE_CUDA(cudaGetLastError());
       }
+  shard_trace().level_mark(h, 4, st);
   return 0;
 }
 
@@ -355,8 +406,11 @@ inline int trtri_merge_sharded(const DenseWork& w, const ShardCtx& cx) {
   for (int h = trtri_hmin(w); h < w.nb; h *= 2) {
     if (level_is_split(cx, h))
       ACE_TRY(trtri_level_sharded(w, 0, w.nb, h, w.main, w.Bf, cx, /*need_lower=*/2 * h < w.nb));
-    else
+    else {
+      for (int k = 0; k < 1; ++k) shard_trace().level_mark(-h, 0, w.main);
       ACE_TRY(trtri_level(w, 0, w.nb, h, w.main, w.Bf));
+      for (int k = 1; k < 5; ++k) shard_trace().level_mark(-h, k, w.main);
+    }
   }
   return 0;
 }
