@@ -288,7 +288,8 @@ struct Core {
   bool shard_dense = false;    // on by default for a sharded fit (ACE_SHARD_DENSE=0: redundant dense phases)
   bool shard_emulate = false;  // one process plays all ranks in turn (single-GPU tests), no NCCL
   int shard_hmin = 16;
-  bool kinv_partial = false;   // Bf holds only this rank's tiles of K^-1 (U is complete in A)
+  bool kinv_partial = false;   // Bf does not hold the complete stored inverse (U is complete in A): rebuilt on demand
+  bool u_valid = false;        // A / DX / DU hold U = L^-T, X = L^-1 of the stored inverse (after an iteration)
   DBuf<double> tvy, tv1, pdg, kdg;
   bool shard_potrf = false;    // panel-cyclic Cholesky with panel broadcasts (ACE_SHARD_POTRF=0: redundant potrf)
   std::vector<cudaEvent_t> shard_events;
@@ -311,8 +312,6 @@ struct Core {
     shard_dense = e ? (std::atoi(e) != 0) : true;
     if (const char* h = std::getenv("ACE_SHARD_HMIN")) shard_hmin = std::max(1, std::atoi(h));
     if (shard_dense) {
-      ACE_TRY(tvy.alloc(n_pad));
-      ACE_TRY(tv1.alloc(n_pad));
       ACE_TRY(pdg.alloc((size_t)n_pad * nchunks));
       ACE_TRY(kdg.alloc(n_pad));
       const char* sp = std::getenv("ACE_SHARD_POTRF");
@@ -436,6 +435,8 @@ struct Core {
       ACE_TRY(ps.alloc(N * nchunks));
       ACE_TRY(partials.alloc((size_t)gp.gx * gp.gy * P));
       if (!dvec.p) ACE_TRY(dvec.alloc(N));
+      ACE_TRY(tvy.alloc(N));  // U^T y, U^T 1: posterior in factor form, alpha of a sharded fit
+      ACE_TRY(tv1.alloc(N));
     }
     return 0;
   }
@@ -559,9 +560,10 @@ struct Core {
   }
 
   int enqueue_finalize(const double* Kinv, const ace_fit_config& c, int do_update, bool reduced = false,
-                       const double* kdiag = nullptr) {
+                       const double* kdiag = nullptr, const double* dvec_alt = nullptr) {
     FinalizeArgs f{};
-    f.partials = partials.p; f.nparts = gp.gx * gp.gy; f.y = y.p; f.alpha = alpha.p; f.Ka = ka(); f.dvec = dvec.p;
+    f.partials = partials.p; f.nparts = gp.gx * gp.gy; f.y = y.p; f.alpha = alpha.p; f.Ka = ka();
+    f.dvec = dvec_alt ? dvec_alt : dvec.p;
     if (reduced) {  // sharded iteration: the all-reduced sums live in red[0..P)
       f.partials = red.p;
       f.nparts = 1;
@@ -684,6 +686,7 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
   }
   ACE_TRY(c.enqueue_finalize(c.Bf.p, f->cfg, 1, sharded, sdense ? c.kdg.p : nullptr));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[5], c.st));
+  c.u_valid = true;
   return 0;
 }
 
@@ -845,16 +848,29 @@ int ace_fit_get_train_stats(ace_fit* f, double* stats) {
   if (!f || !stats) return usage("null argument");
   Core& c = f->c;
   ACE_CUDA(cudaSetDevice(c.device));
-  ACE_TRY(c.ensure_full_inverse());  // needs U, which the rebuild below overwrites
-  DBuf<double> B2;  // local inverse: the stored invKmatn (c.Bf) must stay as it is (quirk Q6)
+  // Local factorisation of K(theta_final): the STORED inverse must stay as it is (quirk Q6).  It is kept in factor
+  // form -- U, X in A with the DX / DU tiles, which the posterior uses directly -- so this runs in other buffers:
+  // Bf takes the new factor (the stored K^-1 is rebuilt from U on demand), B2 its workspace / inverse.
+  DBuf<double> B2, DX2, DU2, dv2;
   ACE_TRY(B2.alloc((size_t)c.n_pad * c.n_pad));
-  DenseWork w = c.dense(c.A.p, B2.p);
+  double* Fac = c.Bf.p;
+  DenseWork w = c.dense(Fac, B2.p);
+  if (c.u_valid) {
+    ACE_TRY(DX2.alloc((size_t)c.n_pad * TB));
+    ACE_TRY(DU2.alloc((size_t)c.n_pad * TB));
+    ACE_TRY(dv2.alloc(c.n_pad));
+    w.DX = DX2.p; w.DU = DU2.p; w.dvec = dv2.p;
+    c.kinv_partial = true;
+  } else {  // nothing stored yet: plain buffers
+    Fac = c.A.p;
+    w = c.dense(Fac, B2.p);
+  }
   ACE_TRY(c.enqueue_prep());
-  ACE_TRY(c.enqueue_build_sym(c.A.p, 1, nullptr, 0));
+  ACE_TRY(c.enqueue_build_sym(Fac, 1, nullptr, 0));
   ACE_TRY(spd_inverse(w));
   ACE_TRY(c.enqueue_alpha(B2.p, 0));
   ACE_TRY(c.enqueue_grad(B2.p));
-  ACE_TRY(c.enqueue_finalize(B2.p, f->cfg, 0));
+  ACE_TRY(c.enqueue_finalize(B2.p, f->cfg, 0, false, nullptr, w.dvec));
   ACE_TRY(c.fetch_scalars());
   stats[0] = c.h_sc[SC_RMSE];
   stats[1] = c.h_sc[SC_EVID];
@@ -1128,6 +1144,33 @@ static int posterior_rows(Core& c, const double* Kinv, const double* Kx, const d
   return 0;
 }
 
+// The same rows from the factor: W = Kx * U (ONE triangular product, half the flops of Kx * K^-1 and no K^-1 at
+// all), mean = W (U^T (y - mu)), T Kx^T = rowsum(W^2).  Afac: lower = X = L^-1, diagonal tiles in DX; upper = U, DU.
+static int posterior_rows_tri(Core& c, const double* Kx, const double* kdiag, int nx, int nx_pad, double mu,
+                              double noise, PostOut& o) {
+  const int n = c.n, n_pad = c.n_pad;
+  ACE_TRY(o.T.alloc((size_t)nx_pad * n_pad));
+  GemmNT g{};
+  g.A = Kx; g.lda = nx_pad; g.B = c.A.p; g.ldb = n_pad; g.b_tri = 2; g.Bdiag = c.DX.p;
+  g.C = o.T.p; g.ldc = nx_pad;
+  g.M = nx_pad; g.N = n_pad; g.K = n_pad; g.alpha = 1.0; g.beta = 0.0;
+  ACE_TRY(launch_gemm_nt(g, c.st));
+  utv2_kernel<<<(n_pad + 7) / 8, 256, 0, c.st>>>(c.A.p, n_pad, c.DU.p, n, n_pad, c.y.p, c.tvy.p, c.tv1.p);
+  ACE_CUDA(cudaGetLastError());
+  const int chunks = (n + pk::CHUNK - 1) / pk::CHUNK;
+  ACE_TRY(o.p1.alloc((size_t)nx_pad * chunks));
+  ACE_TRY(o.p2.alloc((size_t)nx_pad * chunks));
+  ACE_TRY(o.map.alloc(nx_pad));
+  ACE_TRY(o.var.alloc(nx_pad));
+  dim3 grid((nx_pad + pk::ROWS - 1) / pk::ROWS, chunks);
+  rowdot_tri_kernel<<<grid, pk::ROWS, 0, c.st>>>(o.T.p, nx_pad, nx_pad, n, c.tvy.p, c.tv1.p, mu, o.p1.p, o.p2.p);
+  ACE_CUDA(cudaGetLastError());
+  post_finish_kernel<<<(nx_pad + 255) / 256, 256, 0, c.st>>>(o.p1.p, o.p2.p, chunks, nx, nx_pad, kdiag, noise,
+                                                            o.map.p, o.var.p);
+  ACE_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace ace
 
 extern "C" {
@@ -1161,8 +1204,12 @@ int ace_fit_predict(ace_fit* f, const double* X2, const double* Z2, int nx, doub
   ACE_CUDA(cudaMemcpyAsync(hpar, c.theta.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c.st));
   ACE_CUDA(cudaStreamSynchronize(c.st));
   PostOut o;
-  ACE_TRY(c.ensure_full_inverse());
-  ACE_TRY(posterior_rows(c, c.Bf.p, Kx.p, kd.p, nx, nx_pad, hpar[1], std::exp(hpar[0]), o));
+  if (c.u_valid) {
+    ACE_TRY(posterior_rows_tri(c, Kx.p, kd.p, nx, nx_pad, hpar[1], std::exp(hpar[0]), o));
+  } else {
+    ACE_TRY(c.ensure_full_inverse());
+    ACE_TRY(posterior_rows(c, c.Bf.p, Kx.p, kd.p, nx, nx_pad, hpar[1], std::exp(hpar[0]), o));
+  }
   std::vector<double> hm(nx), hv(nx);
   ACE_CUDA(cudaMemcpyAsync(hm.data(), o.map.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));
   ACE_CUDA(cudaMemcpyAsync(hv.data(), o.var.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));

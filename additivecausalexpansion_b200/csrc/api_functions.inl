@@ -224,6 +224,7 @@ int ace_pred_cpp(const double* y_X, double sigma, double mu, const double* invK_
 namespace ace {
 
 // common tail of the marginal prediction: Kx (nx_pad x n_pad), Cm (nx_pad x nx_pad, the marginal K_xx) on device
+// Kinv == nullptr: factor form (posterior_rows_tri), T K_xX^T = W W^T
 static int marginal_tail(Core& c, const double* Kinv, const double* Kx, double* Cm, const double* zx_dev, int nx,
                          int nx_pad, double mu, double std_y, double std_Z, int calculate_ate, const double* Zx_host,
                          double* map, double* ci, double* var, double* avg) {
@@ -233,12 +234,15 @@ static int marginal_tail(Core& c, const double* Kinv, const double* Kx, double* 
   diag_extract_kernel<<<(nx + 255) / 256, 256, 0, c.st>>>(Cm, nx_pad, nx, kd.p);
   ACE_CUDA(cudaGetLastError());
   PostOut o;
-  ACE_TRY(posterior_rows(c, Kinv, Kx, kd.p, nx, nx_pad, mu, 0.0, o));
+  if (Kinv != nullptr)
+    ACE_TRY(posterior_rows(c, Kinv, Kx, kd.p, nx, nx_pad, mu, 0.0, o));
+  else
+    ACE_TRY(posterior_rows_tri(c, Kx, kd.p, nx, nx_pad, mu, 0.0, o));
   double hq[3] = {0, 0, 0};
   if (calculate_ate) {
     // C = K_m,xx - T K_m,xX^T  (src/pred_cpp.cpp:72), full block because the averages need it
     GemmNT g{};
-    g.A = o.T.p; g.lda = nx_pad; g.B = Kx; g.ldb = nx_pad; g.C = Cm; g.ldc = nx_pad;
+    g.A = o.T.p; g.lda = nx_pad; g.B = (Kinv != nullptr) ? Kx : o.T.p; g.ldb = nx_pad; g.C = Cm; g.ldc = nx_pad;
     g.M = nx_pad; g.N = nx_pad; g.K = c.n_pad; g.alpha = -1.0; g.beta = 1.0;
     ACE_TRY(launch_gemm_nt(g, c.st));
     quadforms_kernel<<<1, 1024, 0, c.st>>>(Cm, nx_pad, nx, zx_dev, q.p);
@@ -364,8 +368,8 @@ int ace_fit_predict_marginal(ace_fit* f, const double* X2, const double* Z2, con
   double hpar[2];
   ACE_CUDA(cudaMemcpyAsync(hpar, c.theta.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c.st));
   ACE_TRY(sync_stream(c.st));
-  ACE_TRY(c.ensure_full_inverse());
-  return marginal_tail(c, c.Bf.p, Kx.p, Cm.p, zx.p, nx, nx_pad, hpar[1], std_y, std_Z, calculate_ate, Z2, map, ci,
+  if (!c.u_valid) ACE_TRY(c.ensure_full_inverse());
+  return marginal_tail(c, c.u_valid ? nullptr : c.Bf.p, Kx.p, Cm.p, zx.p, nx, nx_pad, hpar[1], std_y, std_Z, calculate_ate, Z2, map, ci,
                        var, avg);
 }
 

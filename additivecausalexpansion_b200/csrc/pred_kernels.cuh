@@ -49,6 +49,42 @@ __global__ void __launch_bounds__(pk::ROWS) rowdot2_kernel(const double* __restr
   p2[(size_t)blockIdx.y * nx_pad + i] = s2;
 }
 
+// Factor form of the same rows, W = K_xX U with K^-1 = U U^T:  p1[c][i] = sum_j W(i,j) t_j with t = U^T (y - mu) given
+// as ty - mu * t1;  p2[c][i] = sum_j W(i,j)^2  (= the row of T K_xX^T)
+__global__ void __launch_bounds__(pk::ROWS) rowdot_tri_kernel(const double* __restrict__ W, long ld, int nx_pad, int n,
+                                                              const double* __restrict__ ty,
+                                                              const double* __restrict__ t1, double mu,
+                                                              double* __restrict__ p1, double* __restrict__ p2) {
+  using namespace pk;
+  __shared__ double tb[CHUNK];
+  const int i = blockIdx.x * ROWS + threadIdx.x;
+  const int c0 = blockIdx.y * CHUNK;
+  const int cend = min(CHUNK, n - c0);
+  for (int t = threadIdx.x; t < CHUNK; t += ROWS) tb[t] = (t < cend) ? (ty[c0 + t] - mu * t1[c0 + t]) : 0.0;
+  __syncthreads();
+  if (i >= nx_pad) return;
+  const double* wp = W + i + (size_t)c0 * ld;
+  double s1 = 0.0, s2 = 0.0;
+  int t = 0;
+  for (; t + 8 <= cend; t += 8) {
+    double a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = wp[(size_t)(t + e) * ld];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      s1 = fma(a[e], tb[t + e], s1);
+      s2 = fma(a[e], a[e], s2);
+    }
+  }
+  for (; t < cend; ++t) {
+    const double a = wp[(size_t)t * ld];
+    s1 = fma(a, tb[t], s1);
+    s2 = fma(a, a, s2);
+  }
+  p1[(size_t)blockIdx.y * nx_pad + i] = s1;
+  p2[(size_t)blockIdx.y * nx_pad + i] = s2;
+}
+
 // map_raw[i] = T (y - mu);  var_raw[i] = k(x_i,x_i) - T K_xX^T + noise
 __global__ void post_finish_kernel(const double* __restrict__ p1, const double* __restrict__ p2, int chunks, int nx,
                                    int nx_pad, const double* __restrict__ kdiag, double noise,

@@ -405,7 +405,7 @@ inline int trtri_level_sharded(const DenseWork& w, int lo, int len, int h, cudaS
 inline int trtri_merge_sharded(const DenseWork& w, const ShardCtx& cx) {
   for (int h = trtri_hmin(w); h < w.nb; h *= 2) {
     if (level_is_split(cx, h))
-      ACE_TRY(trtri_level_sharded(w, 0, w.nb, h, w.main, w.Bf, cx, /*need_lower=*/2 * h < w.nb));
+      ACE_TRY(trtri_level_sharded(w, 0, w.nb, h, w.main, w.Bf, cx, /*need_lower=*/true));  // X complete: posterior in factor form
     else {
       for (int k = 0; k < 1; ++k) shard_trace().level_mark(-h, 0, w.main);
       ACE_TRY(trtri_level(w, 0, w.nb, h, w.main, w.Bf));
