@@ -1180,43 +1180,59 @@ int ace_fit_predict(ace_fit* f, const double* X2, const double* Z2, int nx, doub
   if (!f || !X2 || !Z2 || !map || !ci || !var || nx < 1) return usage("ace_fit_predict: bad argument");
   Core& c = f->c;
   ACE_CUDA(cudaSetDevice(c.device));
-  const int nx_pad = round_up(nx, TB);
-  DBuf<double> dX2, dZ2, dLZ2, Kx, kd;
-  ACE_TRY(dX2.alloc((size_t)nx_pad * c.p));
-  ACE_TRY(dZ2.alloc((size_t)nx_pad * c.Bz));
-  ACE_TRY(dLZ2.alloc((size_t)nx_pad * c.Bz));
-  ACE_TRY(Kx.alloc((size_t)nx_pad * c.n_pad));
-  ACE_TRY(kd.alloc(nx_pad));
-  ACE_TRY(upload_matrix(dX2.p, nx_pad, nx_pad, X2, nx, c.p, c.st));
-  ACE_TRY(upload_matrix(dZ2.p, nx_pad, nx_pad, Z2, nx, c.Bz, c.st));
-  logabs_kernel<<<(unsigned)(((size_t)nx_pad * c.Bz + 255) / 256), 256, 0, c.st>>>(dZ2.p, dLZ2.p, (size_t)nx_pad * c.Bz);
+  // A sharded fit blocks the test points over the ranks (the factor is replicated, rows are independent);
+  // the raw mean / variance rows are all-gathered, so every rank returns the complete result.  Collective call.
+  const bool split = c.shard_world > 1 && !c.shard_emulate && c.u_valid && f->comm != nullptr;
+  const int G = split ? c.shard_world : 1, r = split ? c.shard_rank : 0;
+  const int chunk = round_up((nx + G - 1) / G, TB);  // rows per rank, on the 128 grid
+  const int nx_all = chunk * G;                       // padded length of the gathered vectors
+  const int lo = std::min(nx, r * chunk), cnt = std::min(nx, lo + chunk) - lo;
+  DBuf<double> dX2, dZ2, dLZ2, Kx, kd, res;
+  ACE_TRY(dX2.alloc((size_t)nx_all * c.p));
+  ACE_TRY(dZ2.alloc((size_t)nx_all * c.Bz));
+  ACE_TRY(dLZ2.alloc((size_t)nx_all * c.Bz));
+  ACE_TRY(Kx.alloc((size_t)chunk * c.n_pad));
+  ACE_TRY(kd.alloc(chunk));
+  ACE_TRY(res.alloc((size_t)2 * nx_all));  // [map of all ranks | var of all ranks]
+  ACE_TRY(upload_matrix(dX2.p, nx_all, nx_all, X2, nx, c.p, c.st));
+  ACE_TRY(upload_matrix(dZ2.p, nx_all, nx_all, Z2, nx, c.Bz, c.st));
+  logabs_kernel<<<(unsigned)(((size_t)nx_all * c.Bz + 255) / 256), 256, 0, c.st>>>(dZ2.p, dLZ2.p, (size_t)nx_all * c.Bz);
   ACE_CUDA(cudaGetLastError());
   ACE_TRY(c.enqueue_prep());  // kernels built from the CURRENT parameters (R/kernel_SE_R6.R:78-79)
   KernArgs a{};
-  a.X1 = dX2.p; a.Z1 = dZ2.p; a.LZ1 = dLZ2.p; a.ld1 = nx_pad;
+  a.X1 = dX2.p + lo; a.Z1 = dZ2.p + lo; a.LZ1 = dLZ2.p + lo; a.ld1 = nx_all;
   a.X2 = c.X.p; a.Z2 = c.Z.p; a.LZ2 = c.LZ.p; a.ld2 = c.n_pad;
-  a.n1 = nx; a.n2 = c.n; a.n1_pad = nx_pad; a.n2_pad = c.n_pad; a.p = c.p; a.B = c.B; a.tab = c.tab.p;
-  a.K = Kx.p; a.ldk = nx_pad;
+  a.n1 = cnt; a.n2 = c.n; a.n1_pad = chunk; a.n2_pad = c.n_pad; a.p = c.p; a.B = c.B; a.tab = c.tab.p;
+  a.K = Kx.p; a.ldk = chunk;
   ACE_TRY(launch_kernmat(a, c.kind, c.st));
-  kdiag_kernel<<<(nx_pad + 255) / 256, 256, 0, c.st>>>(dZ2.p, dLZ2.p, nx_pad, nx, c.B, c.kind, c.tab.p, 0, kd.p);
+  kdiag_kernel<<<(chunk + 255) / 256, 256, 0, c.st>>>(dZ2.p + lo, dLZ2.p + lo, nx_all, cnt, c.B, c.kind, c.tab.p, 0, kd.p);
   ACE_CUDA(cudaGetLastError());
   double hpar[2];
   ACE_CUDA(cudaMemcpyAsync(hpar, c.theta.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, c.st));
   ACE_CUDA(cudaStreamSynchronize(c.st));
   PostOut o;
   if (c.u_valid) {
-    ACE_TRY(posterior_rows_tri(c, Kx.p, kd.p, nx, nx_pad, hpar[1], std::exp(hpar[0]), o));
+    ACE_TRY(posterior_rows_tri(c, Kx.p, kd.p, cnt, chunk, hpar[1], std::exp(hpar[0]), o));
   } else {
     ACE_TRY(c.ensure_full_inverse());
-    ACE_TRY(posterior_rows(c, c.Bf.p, Kx.p, kd.p, nx, nx_pad, hpar[1], std::exp(hpar[0]), o));
+    ACE_TRY(posterior_rows(c, c.Bf.p, Kx.p, kd.p, cnt, chunk, hpar[1], std::exp(hpar[0]), o));
   }
-  std::vector<double> hm(nx), hv(nx);
-  ACE_CUDA(cudaMemcpyAsync(hm.data(), o.map.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));
-  ACE_CUDA(cudaMemcpyAsync(hv.data(), o.var.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));
+  ACE_CUDA(cudaMemcpyAsync(res.p + (size_t)r * chunk, o.map.p, sizeof(double) * chunk, cudaMemcpyDeviceToDevice, c.st));
+  ACE_CUDA(cudaMemcpyAsync(res.p + nx_all + (size_t)r * chunk, o.var.p, sizeof(double) * chunk, cudaMemcpyDeviceToDevice,
+                           c.st));
+  if (split) {
+    NcclApi& nc = nccl_api();
+    ACE_NCCL(nc.GroupStart());
+    ACE_NCCL(nc.AllGather(res.p + (size_t)r * chunk, res.p, chunk, ncclFloat64, f->comm, c.st));
+    ACE_NCCL(nc.AllGather(res.p + nx_all + (size_t)r * chunk, res.p + nx_all, chunk, ncclFloat64, f->comm, c.st));
+    ACE_NCCL(nc.GroupEnd());
+  }
+  std::vector<double> h((size_t)2 * nx_all);
+  ACE_CUDA(cudaMemcpyAsync(h.data(), res.p, sizeof(double) * 2 * nx_all, cudaMemcpyDeviceToHost, c.st));
   ACE_CUDA(cudaStreamSynchronize(c.st));
-  for (int i = 0; i < nx; ++i) {  // src/pred_cpp.cpp:20,26-29
-    map[i] = mean_y + std_y * (hm[i] + hpar[1]);
-    const double sd = std_y * std::sqrt(std::fabs(hv[i]));
+  for (int i = 0; i < nx; ++i) {  // src/pred_cpp.cpp:20,26-29; point i sits at i (rank block i / chunk, offset i % chunk)
+    map[i] = mean_y + std_y * (h[i] + hpar[1]);
+    const double sd = std_y * std::sqrt(std::fabs(h[(size_t)nx_all + i]));
     ci[i] = map[i] - 1.96 * sd;
     ci[i + nx] = map[i] + 1.96 * sd;
     var[i] = sd * sd;

@@ -28,6 +28,14 @@ with AceFit(prob.y, prob.X, prob.Z, prob.parameters, kernel=prob.kernel, std_y=p
         f.para_update(it)
     ms_sh = f.timer_stop() / 3
     ph = f.last_timing_ms
+    # posterior of the sharded fit (collective: the test points are blocked over the ranks)
+    rng = np.random.default_rng(7)
+    nx = 1000
+    X2 = np.asfortranarray(rng.uniform(-1, 1, (nx, prob.p))); z2 = rng.uniform(-1, 1, nx)
+    tb = prob.basis.testbasis(z2)
+    torch.cuda.synchronize(); dist.barrier()
+    import time as _t
+    t0 = _t.time(); pred_sh = f.predict(X2, tb["B"], prob.mean_y, prob.std_y); t_pred_sh = _t.time() - t0
     if os.environ.get("ACE_SHARD_TRACE") and rank in (0, 1):
         from additivecausalexpansion_b200._lib import lib
         lib().ace_dbg_shard_trace_dump(rank)
@@ -50,6 +58,10 @@ if rank == 0:
         for it in range(K + 1, K + 4):
             g.para_update(it)
         ms_1 = g.timer_stop() / 3
+        t0 = _t.time(); pred_1 = g.predict(X2, tb["B"], prob.mean_y, prob.std_y); t_pred_1 = _t.time() - t0
+        out["predict"] = {"nx": nx, "map_rel": float(np.abs(pred_sh["map"] - pred_1["map"]).max() / np.abs(pred_1["map"]).max()),
+                          "var_rel": float(np.abs(pred_sh["var"] - pred_1["var"]).max() / np.abs(pred_1["var"]).max()),
+                          "wall_s_sharded": t_pred_sh, "wall_s_single": t_pred_1}
         out.update({"ms_per_iter_sharded": ms_sh, "ms_per_iter_single": ms_1, "speedup": ms_1 / ms_sh, "phases_sharded": ph, "phases_single": g.last_timing_ms})
     print(json.dumps(out, default=float))
     json.dump(out, open(f"/root/repo/gpurun_out/shard_check_{cfg}_w{world}.json", "w"), indent=1, default=float)

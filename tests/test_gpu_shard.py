@@ -25,3 +25,4 @@ def test_sharded_fit_matches_single_gpu():
     assert res["params_bit_identical_across_ranks"]
     for it in res["iters"]:
         assert it["evid_rel"] <= 1e-12 and it["grad_rel"] <= 1e-9 and it["par_abs"] <= 1e-10
+    assert res["predict"]["map_rel"] <= 1e-9 and res["predict"]["var_rel"] <= 1e-8
