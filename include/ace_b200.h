@@ -187,7 +187,9 @@ int ace_fit_dims(ace_fit* fit, int* n, int* p, int* B, int* P);
 int ace_fit_last_timing(ace_fit* fit, double* ms6);
 
 /* Kernel$predict (R/kernel_SE_R6.R:75-83): posterior mean / CI / variance at nx new points with the
- * stored invKmatn and the CURRENT parameters.  X2: nx x p, Z2: nx x Bz. */
+ * stored invKmatn and the CURRENT parameters.  X2: nx x p, Z2: nx x Bz.  After an iteration the stored inverse is
+ * used in factor form (W = K_xX U, K^-1 = U U^T).  On a sharded fit this is a COLLECTIVE call: the test points are
+ * blocked over the ranks and the rows all-gathered, every rank returns the complete result. */
 int ace_fit_predict(ace_fit* fit, const double* X2, const double* Z2, int nx, double mean_y, double std_y,
                     double* map, double* ci, double* var);
 /* Kernel$predict_marginal (R/kernel_SE_R6.R:84-97).  Z2: nx x Bz basis at the new points (its first
