@@ -269,7 +269,7 @@ static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStre
 struct Core {
   int device = 0, sms = 148;
   int n = 0, n_pad = 0, p = 0, Bz = 0, B = 0, P = 0, kind = 0;
-  cudaStream_t st = nullptr, side = nullptr, aux = nullptr;
+  cudaStream_t st = nullptr, side = nullptr, aux = nullptr, bgst = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   DBuf<double> Wp0, Wp1, Wsmall;  // fused panel TRSM workspaces (chol.cuh)
   int panel_blocks = 4;
@@ -362,6 +362,7 @@ struct Core {
     if (st) cudaStreamDestroy(st);
     if (side) cudaStreamDestroy(side);
     if (aux) cudaStreamDestroy(aux);
+    if (bgst) cudaStreamDestroy(bgst);
   }
 
   int init(int dev, int n_, int p_, int Bz_, int kind_, bool need_dense, bool need_grad) {
@@ -383,6 +384,7 @@ struct Core {
     ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     ACE_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));  // panel stream: high priority
     ACE_CUDA(cudaStreamCreateWithPriority(&aux, cudaStreamNonBlocking, lo));   // filler work: lowest priority
+    ACE_CUDA(cudaStreamCreateWithPriority(&bgst, cudaStreamNonBlocking, lo));  // incremental inverse behind the panels
     for (auto& e : ev) ACE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : tev) ACE_CUDA(cudaEventCreate(&e));
     ACE_CUDA(cudaMallocHost(&h_sc, sizeof(double) * (SC_COUNT + 2)));
@@ -415,9 +417,10 @@ struct Core {
       }
       const char* fu = std::getenv("ACE_FUSED_TRSM");
       const bool pow2 = (panel_blocks & (panel_blocks - 1)) == 0;
-      // measured: the fused panel TRSM pays off from n ~ 12k (16384: 54.2 -> 53.2 ms, 32768: 359 -> 355 ms) and
-      // costs ~0.4 ms below (8192: 13.3 -> 13.8 ms), so it is on for n_pad >= 12288 unless ACE_FUSED_TRSM says otherwise
-      const bool want = fu ? (std::atoi(fu) != 0) : (n_pad >= 12288);
+      // The fused panel TRSM (early X_JJ) also enables the incremental inverse behind the panels (chol.cuh); together
+      // they pay off at every size measured: C2 (n=4096) 8.65 -> 7.87 ms, C5 (n=8192) 27.0 -> 23.5 ms, C3 (n=16384)
+      // 164.9 -> 158.3 ms per iteration.  ACE_FUSED_TRSM=0 switches both off.
+      const bool want = fu ? (std::atoi(fu) != 0) : (n_pad >= 1024);
       if (pow2 && panel_blocks >= 2 && want) {
         ACE_TRY(Wp0.alloc(N * panel_blocks * TB));
         ACE_TRY(Wp1.alloc(N * panel_blocks * TB));
@@ -465,7 +468,7 @@ struct Core {
       w.Wp[0] = Wp0.p; w.Wp[1] = Wp1.p; w.Wsmall = Wsmall.p; w.ev_copy[0] = ev[6]; w.ev_copy[1] = ev[7];
     }
     w.A = Abuf; w.ld = n_pad; w.nb = n_pad / TB; w.DX = DX.p; w.DU = DU.p; w.dvec = dvec.p; w.info = info.p;
-    w.Bf = Bbuf; w.main = st; w.side = side; w.aux = aux; w.ev_half = ev[4]; w.ev_aux = ev[5];
+    w.Bf = Bbuf; w.main = st; w.side = side; w.aux = aux; w.bg = bgst; w.ev_half = ev[4]; w.ev_aux = ev[5];
     w.ev_panel[0] = ev[0]; w.ev_panel[1] = ev[1]; w.ev_upd[0] = ev[2]; w.ev_upd[1] = ev[3];
 
     return w;

@@ -299,6 +299,7 @@ struct DenseWork {
   int* info = nullptr;     // device int: 0, or 1-based index of the first non-positive pivot
   double* Bf = nullptr;    // n_pad x n_pad: workspace, then the inverse
   cudaStream_t main = nullptr, side = nullptr, aux = nullptr;
+  cudaStream_t bg = nullptr;  // background stream of the incremental inverse (lowest priority)
   cudaEvent_t ev_panel[2] = {nullptr, nullptr}, ev_upd[2] = {nullptr, nullptr};
   cudaEvent_t ev_half = nullptr, ev_aux = nullptr;  // overlap of the leading block's inverse with the potrf tail
   int panel_blocks = 4;    // look-ahead panel width in 128-blocks (512 columns)
@@ -374,7 +375,7 @@ inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st
 // started on the aux stream (it only touches A[0:fork_at, 0:fork_at], which potrf never reads again); the
 // caller joins on ev_aux.  The tail of a Cholesky is latency bound (a chain of 128-wide leaf kernels with
 // almost no trailing work), so this fills otherwise idle SMs.
-inline int potrf_blocked(const DenseWork& w, int fork_at = 0, int fork_when = 0) {
+inline int potrf_blocked(const DenseWork& w, int fork_at = 0, int fork_when = 0, bool incremental = false) {
   const int nb = w.nb, pb = w.panel_blocks;
   bool forked = false;
   ACE_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int), w.main));
@@ -419,6 +420,30 @@ inline int potrf_blocked(const DenseWork& w, int fork_at = 0, int fork_when = 0)
                                  sizeof(double) * w.ld, sizeof(double) * (size_t)(nb - j1) * TB, (size_t)(j1 - j0) * TB,
                                  cudaMemcpyDeviceToDevice, w.aux));
       ACE_CUDA(cudaEventRecord(w.ev_copy[J & 1], w.aux));
+    }
+    if (incremental && fused && J >= 1) {
+      // Incremental inverse: as soon as block row J of L is final and X_JJ is known, the rows X[J, 0:j0] follow
+      // from the leading inverse -- the merge of [0,j0) with [j0,j1) -- on the low-priority stream, filling the
+      // SM time the latency-bound panel chain leaves idle.  In stream order after all earlier merges and copies.
+      cudaStream_t bg = w.bg ? w.bg : w.aux;
+      ACE_CUDA(cudaStreamWaitEvent(bg, w.ev_panel[J & 1], 0));        // X_JJ
+      ACE_CUDA(cudaStreamWaitEvent(bg, w.ev_copy[(J - 1) & 1], 0));   // block row J of L is in A (copies are in order)
+      const int s1 = j0 * TB, s2 = (j1 - j0) * TB;
+      GemmNT p{};
+      p.A = w.A; p.lda = w.ld; p.a_tri = 1; p.Adiag = w.DU;
+      p.B = blkptr(w, j0, 0); p.ldb = w.ld;
+      p.C = w.Bf; p.ldc = s1;
+      p.M = s1; p.N = s2; p.K = s1; p.alpha = 1.0; p.beta = 0.0;
+      ACE_TRY(launch_gemm_nt(p, bg));
+      GemmNT r{};
+      r.A = blkptr(w, j0, j0); r.lda = w.ld; r.a_tri = 2; r.Adiag = w.DX + (size_t)j0 * TB * TB;
+      r.B = w.Bf; r.ldb = s1;
+      r.C = blkptr(w, j0, 0); r.ldc = w.ld;
+      r.Ct = blkptr(w, 0, j0); r.ldct = w.ld;
+      r.M = s2; r.N = s1; r.K = s2; r.alpha = -1.0; r.beta = 0.0;
+      ACE_TRY(launch_gemm_nt(r, bg));
+      ACE_CUDA(cudaEventRecord(w.ev_aux, bg));
+      forked = true;
     }
     if (fork_at > 0 && !forked && j1 >= fork_at && j1 >= fork_when && j1 < nb) {
       ACE_CUDA(cudaEventRecord(w.ev_half, w.side));
@@ -526,6 +551,15 @@ inline int potrf_trtri(const DenseWork& w) {
     int s = potrf_blocked(w);
     if (s < 0) return s;
     return trtri_merge(w);
+  }
+  // default: incremental inverse behind the panels whenever the fused panel path (early X_JJ) is on; measured at
+  // n = 16384: potrf + trtri 95.5 -> 88.4 ms (ACE_INCR_TRTRI=0 restores the fork-at-3/4 schedule below)
+  static const int incr = std::getenv("ACE_INCR_TRTRI") ? std::atoi(std::getenv("ACE_INCR_TRTRI")) : 1;
+  if (incr && w.Wp[0] != nullptr) {
+    const int forked = potrf_blocked(w, 0, 0, true);
+    if (forked < 0) return forked;
+    if (forked) ACE_CUDA(cudaStreamWaitEvent(w.main, w.ev_aux, 0));
+    return 0;  // X, U complete: every merge ran behind its panel
   }
   // the leading block is final after panel h_top/pb, but its inverse is only released once the trailing
   // updates have become small (last ~quarter of the columns): released earlier it merely competes with them
