@@ -291,6 +291,7 @@ struct Core {
   bool kinv_partial = false;   // Bf does not hold the complete stored inverse (U is complete in A): rebuilt on demand
   bool u_valid = false;        // A / DX / DU hold U = L^-T, X = L^-1 of the stored inverse (after an iteration)
   DBuf<double> tvy, tv1, pdg, kdg;
+  bool shard_incr = true;      // inverse grown behind the panels, column panels per rank (ACE_SHARD_INCR=0: split merge tree)
   bool shard_potrf = false;    // panel-cyclic Cholesky with panel broadcasts (ACE_SHARD_POTRF=0: redundant potrf)
   std::vector<cudaEvent_t> shard_events;
   DBuf<double> head0, head1;   // packed panel heads (shard_dense.cuh)
@@ -303,6 +304,7 @@ struct Core {
     cx.comm2 = comm2;
     cx.events = const_cast<cudaEvent_t*>(shard_events.data());
     cx.head[0] = head0.p; cx.head[1] = head1.p; cx.bulk_stream = bulk;
+    cx.incr = shard_incr;
     return cx;
   }
   int alloc_shard() {
@@ -338,6 +340,7 @@ struct Core {
           shard_events.push_back(e);
         }
         shard_potrf = true;
+        if (const char* si = std::getenv("ACE_SHARD_INCR")) shard_incr = std::atoi(si) != 0;
       }
     }
     return 0;
@@ -667,7 +670,10 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
       if (s < 0) return s;
     }
     if (timed) ACE_CUDA(cudaEventRecord(c.tev[2], c.st));
-    ACE_TRY(trtri_merge_sharded(w, cx));
+    if (spotrf && cx.incr)
+      ACE_TRY(gather_inverse_sharded(w, cx));
+    else
+      ACE_TRY(trtri_merge_sharded(w, cx));
     if (timed) ACE_CUDA(cudaEventRecord(c.tev[3], c.st));
     ACE_TRY(uut_inverse_sharded(w, cx));
     if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));

@@ -48,6 +48,7 @@ struct GemmNT {
   // A is a row slice starting at row a_row_off (multiple of 128) of the triangular operand: the k trimming and
   // the diagonal-tile redirect use the row block index ti + a_row_off/128 (Adiag stays the unshifted tile array)
   int a_row_off;
+  int s_row_off;        // batched: problem q uses a_row_off + q * s_row_off
   // strided batch (blockIdx.y): problem q uses every pointer advanced by q * its stride (elements)
   int batch;            // 0 or 1: single problem
   long sA, sB, sC, sCt, sAdiag, sBdiag;
@@ -109,9 +110,10 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
   const int i0 = ti * BM, j0 = tj * BN;
   if (i0 >= p.M - (int)q * p.m_dec) return;  // whole CTA, before any barrier exists
   int k_begin = 0, k_end = p.K;
-  const int tia = ti + p.a_row_off / TB;  // row block of this tile inside the (possibly sliced) A operand
-  if (p.a_tri == 1) k_begin = i0 + p.a_row_off;
-  if (p.a_tri == 2) k_end = i0 + p.a_row_off + BM;
+  const int a_off = p.a_row_off + (int)q * p.s_row_off;
+  const int tia = ti + a_off / TB;  // row block of this tile inside the (possibly sliced) A operand
+  if (p.a_tri == 1) k_begin = i0 + a_off;
+  if (p.a_tri == 2) k_end = i0 + a_off + BM;
   if (p.b_tri == 2) k_end = min(k_end, (j0 / TB + 1) * TB);
   const int nchunks = (k_end - k_begin) / BK;
 
@@ -249,7 +251,7 @@ inline int launch_gemm_nt(const GemmNT& p, cudaStream_t stream) {
     tiles = (tiles - p.tile_first + p.tile_stride - 1) / p.tile_stride;
     if (tiles <= 0) return 0;
   }
-  if (p.a_row_off % TB) {
+  if (p.a_row_off % TB || p.s_row_off % TB) {
     set_error("launch_gemm_nt: a_row_off must be a multiple of 128");
     return -2;
   }

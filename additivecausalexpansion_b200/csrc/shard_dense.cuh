@@ -38,6 +38,7 @@ struct ShardCtx {
   cudaEvent_t* events = nullptr;    // SHARD_EVENT_KINDS * panels events of potrf_sharded
   double* head[2] = {nullptr, nullptr};  // packed panel heads, (2 * panel width) x (panel width) doubles each
   cudaStream_t bulk_stream = nullptr;
+  bool incr = false;  // incremental inverse behind the panels: every rank grows X[:, its column panels] in the background
   bool mine(int panel) const { return emulate || panel % world == rank; }
 };
 
@@ -233,6 +234,36 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
                                    sizeof(double) * mB, (size_t)wJ, cudaMemcpyDeviceToDevice, w.aux));
     }
     ACE_CUDA(cudaEventRecord(ev_copy[J], w.aux));
+    // ================= background stream: rows J of the inverse for MY column panels c < J,
+    //   X[J, c] = -X_JJ * ( L[J, c0:j0] * X[c0:j0, c] ),
+    // as two batched GEMMs over the owned panels (Wt_c = U[c rows, c0:j0] * L[J, c0:j0]^T; X[J,c] = -X_JJ Wt_c^T,
+    // with the transposed copy U[c rows, J]).  A rank only ever needs its own columns of X: no exchange until the end.
+    if (cx.incr && J >= 1 && w.bg) {
+      const int Gs = cx.emulate ? 1 : cx.world;
+      const int cf = cx.emulate ? 0 : cx.rank;
+      const int cnt = (cf < J) ? (J - cf + Gs - 1) / Gs : 0;
+      ACE_CUDA(cudaStreamWaitEvent(w.bg, ev_copy[J], 0));  // block row J of L and X_JJ are in A (copies are in order)
+      if (cnt > 0) {
+        const long pw = (long)pb * TB, step = (long)Gs * pw;
+        GemmNT p{};
+        p.A = w.A + (size_t)cf * pw; p.lda = w.ld; p.a_tri = 1; p.a_row_off = (int)(cf * pw); p.s_row_off = (int)step;
+        p.Adiag = w.DU;
+        p.B = blkptr(w, j0, 0); p.ldb = w.ld;
+        p.C = w.Bf; p.ldc = pw;
+        p.M = (int)pw; p.N = (int)wJ; p.K = j0 * TB; p.alpha = 1.0; p.beta = 0.0;
+        p.batch = cnt; p.sA = step; p.sB = 0; p.sC = pw * wJ;
+        ACE_TRY(launch_gemm_nt(p, w.bg));
+        GemmNT r{};
+        r.A = blkptr(w, j0, j0); r.lda = w.ld; r.a_tri = 2; r.Adiag = w.DX + (size_t)j0 * TB * TB;
+        r.B = w.Bf; r.ldb = pw;
+        r.C = blkptr(w, j0, cf * pb); r.ldc = w.ld;
+        r.Ct = blkptr(w, cf * pb, j0); r.ldct = w.ld;
+        r.M = (int)wJ; r.N = (int)pw; r.K = (int)wJ; r.alpha = -1.0; r.beta = 0.0;
+        r.batch = cnt; r.sA = 0; r.sB = pw * wJ; r.sC = step * w.ld; r.sCt = step;
+        ACE_TRY(launch_gemm_nt(r, w.bg));
+      }
+      ACE_CUDA(cudaEventRecord(w.ev_aux, w.bg));
+    }
     // ================= main stream: panel J applied to the rest of my panels (all below row j2: bulk operands)
     ACE_CUDA(cudaStreamWaitEvent(w.main, ev_bulk[J], 0));
     tr.mark(J, 7, w.main);
@@ -398,6 +429,56 @@ inline int trtri_level_sharded(const DenseWork& w, int lo, int len, int h, cudaS
         ACE_CUDA(cudaGetLastError());
       }
   shard_trace().level_mark(h, 4, st);
+  return 0;
+}
+
+// Phase 2 after an incremental run: the background stream is joined and every rank's column panels of X travel to
+// everybody (packed lower trapezoids, one grouped broadcast per panel), unpacked as X (lower) and U (upper).
+inline int gather_inverse_sharded(const DenseWork& w, const ShardCtx& cx) {
+  const int nb = w.nb, pb = w.panel_blocks, NP = shard_panels(nb, pb);
+  cudaStream_t st = w.main;
+  if (NP >= 2) ACE_CUDA(cudaStreamWaitEvent(st, w.ev_aux, 0));
+  shard_trace().level_mark(1 << 20, 0, st);
+  // staging = [world][chunk]: rank q's panels packed one after the other in chunk q (chunk = the largest rank total,
+  // i.e. rank 0's: it owns the earliest, tallest panel of every cycle), exchanged with ONE ncclAllGather
+  const int G = cx.world;
+  std::vector<size_t> off(NP, 0), tot(G, 0);
+  for (int c = 0; c < NP; ++c) {
+    const int c0 = c * pb, c1 = std::min(c0 + pb, nb);
+    off[c] = tot[c % G];
+    tot[c % G] += (size_t)(nb - c1) * TB * (size_t)(c1 - c0) * TB;
+  }
+  size_t chunk = 0;
+  for (int q = 0; q < G; ++q) chunk = std::max(chunk, tot[q]);
+  double* stage = w.Bf;
+  if ((size_t)G * chunk > (size_t)w.ld * w.ld) {
+    set_error("gather_inverse_sharded: staging does not fit");
+    return -2;
+  }
+  for (int c = 0; c < NP; ++c) {
+    const int c0 = c * pb, c1 = std::min(c0 + pb, nb);
+    const long mC = (long)(nb - c1) * TB, wC = (long)(c1 - c0) * TB;
+    if (mC == 0 || !cx.mine(c)) continue;
+    ACE_CUDA(cudaMemcpy2DAsync(stage + (size_t)(c % G) * chunk + off[c], sizeof(double) * mC, blkptr(w, c1, c0),
+                               sizeof(double) * w.ld, sizeof(double) * mC, (size_t)wC, cudaMemcpyDeviceToDevice, st));
+  }
+  shard_trace().level_mark(1 << 20, 1, st);
+  shard_trace().level_mark(1 << 20, 2, st);
+  if (!cx.emulate && chunk > 0) {
+    NcclApi& nc = nccl_api();
+    ACE_NCCL(nc.AllGather(stage + (size_t)cx.rank * chunk, stage, chunk, ncclFloat64, cx.comm, st));
+  }
+  shard_trace().level_mark(1 << 20, 3, st);
+  for (int c = 0; c < NP; ++c) {
+    const int c0 = c * pb, c1 = std::min(c0 + pb, nb);
+    const int mC = (nb - c1) * TB, wC = (c1 - c0) * TB;
+    if (mC == 0) continue;
+    dim3 grid(mC / 32, wC / 32);
+    unpack_piece_kernel<<<grid, 256, 0, st>>>(stage + (size_t)(c % G) * chunk + off[c], mC, wC, blkptr(w, c1, c0), w.ld,
+                                              blkptr(w, c0, c1), w.ld);
+    ACE_CUDA(cudaGetLastError());
+  }
+  shard_trace().level_mark(1 << 20, 4, st);
   return 0;
 }
 

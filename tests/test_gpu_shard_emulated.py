@@ -53,10 +53,15 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("incr", [1, 0])
 @pytest.mark.parametrize("n,p,Bz,kernel,world,hmin,spotrf", CASES)
-def test_emulated_sharded_fit_tracks_unsharded(n, p, Bz, kernel, world, hmin, spotrf):
+def test_emulated_sharded_fit_tracks_unsharded(n, p, Bz, kernel, world, hmin, spotrf, incr):
+    """incr 1: the inverse grows behind the Cholesky panels (column panels per rank, one gather at the end);
+    incr 0: split merge tree after the factorisation."""
+    if incr == 0 and spotrf == 0 and hmin > 64:
+        pytest.skip("same path as incr=1 for this case")
     y, X, Z, par = _problem(n, p, Bz, 11 + n)
-    old = _env(ACE_SHARD_HMIN=hmin, ACE_SHARD_DENSE=1, ACE_SHARD_POTRF=spotrf)
+    old = _env(ACE_SHARD_HMIN=hmin, ACE_SHARD_DENSE=1, ACE_SHARD_POTRF=spotrf, ACE_SHARD_INCR=incr)
     try:
         with AceFit(y, X, Z, par, kernel=kernel, use_graph=False) as s, \
                 AceFit(y, X, Z, par, kernel=kernel, use_graph=False) as g:
