@@ -53,6 +53,9 @@ struct GemmNT {
   int batch;            // 0 or 1: single problem
   long sA, sB, sC, sCt, sAdiag, sBdiag;
   int m_dec;            // batched problems of shrinking height: problem q has M - q * m_dec rows (tiles beyond exit)
+  // split-K: batch entry q = problem (q / ksplit), K chunk (q % ksplit) = absolute k in [chunk * klen, (chunk+1) * klen);
+  // A, B, Adiag, Bdiag, a_row_off advance with the problem, C / Ct with the entry (partial results, summed by the caller)
+  int ksplit, klen;
 };
 
 namespace gemm {
@@ -70,11 +73,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
   using namespace gemm;
   // strided batch: every base pointer of problem q = blockIdx.y (plain locals; the parameter struct is
   // never modified)
-  const long q = blockIdx.y;
+  const long qe = blockIdx.y;                                    // batch entry
+  const long q = (p.ksplit > 1) ? qe / p.ksplit : qe;            // problem
+  const int kchunk = (p.ksplit > 1) ? (int)(qe % p.ksplit) : 0;  // its K chunk
   const double* const gA = p.A + q * p.sA;
   const double* const gB = p.B + q * p.sB;
-  double* const gC = p.C + q * p.sC;
-  double* const gCt = (p.Ct != nullptr) ? p.Ct + q * p.sCt : nullptr;
+  double* const gC = p.C + qe * p.sC;
+  double* const gCt = (p.Ct != nullptr) ? p.Ct + qe * p.sCt : nullptr;
   const double* const gAdiag = (p.Adiag != nullptr) ? p.Adiag + q * p.sAdiag : nullptr;
   const double* const gBdiag = (p.Bdiag != nullptr) ? p.Bdiag + q * p.sBdiag : nullptr;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -115,7 +120,11 @@ __global__ void __launch_bounds__(gemm::THREADS, 2) dgemm_nt_kernel(const GemmNT
   if (p.a_tri == 1) k_begin = i0 + a_off;
   if (p.a_tri == 2) k_end = i0 + a_off + BM;
   if (p.b_tri == 2) k_end = min(k_end, (j0 / TB + 1) * TB);
-  const int nchunks = (k_end - k_begin) / BK;
+  if (p.ksplit > 1) {
+    k_begin = max(k_begin, kchunk * p.klen);
+    k_end = min(k_end, (kchunk + 1) * p.klen);
+  }
+  const int nchunks = (k_end - k_begin) / BK;  // <= 0: empty range, the tile stores beta * C (zeros for beta = 0)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -255,7 +264,11 @@ inline int launch_gemm_nt(const GemmNT& p, cudaStream_t stream) {
     set_error("launch_gemm_nt: a_row_off must be a multiple of 128");
     return -2;
   }
-  dim3 grid((unsigned)tiles, (unsigned)(p.batch > 1 ? p.batch : 1));
+  if (p.ksplit > 1 && (p.klen % TB || p.klen <= 0)) {
+    set_error("launch_gemm_nt: split-K chunk must be a positive multiple of 128");
+    return -2;
+  }
+  dim3 grid((unsigned)tiles, (unsigned)((p.batch > 1 ? p.batch : 1) * (p.ksplit > 1 ? p.ksplit : 1)));
   dgemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p);
   ACE_CUDA(cudaGetLastError());
   return 0;

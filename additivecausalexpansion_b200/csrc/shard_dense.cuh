@@ -43,6 +43,19 @@ struct ShardCtx {
 };
 
 inline int shard_panels(int nb, int pb) { return (nb + pb - 1) / pb; }
+
+// out[e] = sum_s part[(prob * S + s) * len + e]: sums the S split-K partials of every problem (len elements each)
+__global__ void __launch_bounds__(256) splitk_sum_kernel(const double* __restrict__ part, int S, size_t len, size_t total,
+                                                         double* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const size_t prob = idx / len, e = idx % len;
+  const double* src = part + prob * (size_t)S * len + e;
+  double acc = src[0];
+  for (int s2 = 1; s2 < S; ++s2) acc += src[(size_t)s2 * len];
+  out[idx] = acc;
+}
+
 constexpr int SHARD_EVENT_KINDS = 7;
 
 // ACE_SHARD_TRACE=1: per-panel timeline of potrf_sharded (CUDA events with timing), printed by shard_trace_dump
@@ -245,14 +258,28 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
       ACE_CUDA(cudaStreamWaitEvent(w.bg, ev_copy[J], 0));  // block row J of L and X_JJ are in A (copies are in order)
       if (cnt > 0) {
         const long pw = (long)pb * TB, step = (long)Gs * pw;
+        // few tiles (32 per problem) with a K range that grows to n: split K into chunks of <= 2048 so that the
+        // background work is spread over the SMs instead of running as a handful of millisecond-long tiles
+        const int KL = 2048;
+        const int S = std::max(1, (j0 * TB + KL - 1) / KL);
+        const size_t len = (size_t)pw * wJ;
+        double* part = (S > 1) ? w.Bf + (size_t)cnt * len : w.Bf;  // partials behind the summed Wt
         GemmNT p{};
         p.A = w.A + (size_t)cf * pw; p.lda = w.ld; p.a_tri = 1; p.a_row_off = (int)(cf * pw); p.s_row_off = (int)step;
         p.Adiag = w.DU;
         p.B = blkptr(w, j0, 0); p.ldb = w.ld;
-        p.C = w.Bf; p.ldc = pw;
+        p.C = part; p.ldc = pw;
         p.M = (int)pw; p.N = (int)wJ; p.K = j0 * TB; p.alpha = 1.0; p.beta = 0.0;
-        p.batch = cnt; p.sA = step; p.sB = 0; p.sC = pw * wJ;
+        p.batch = cnt; p.sA = step; p.sB = 0; p.sC = (long)len;
+        if (S > 1) {
+          p.ksplit = S; p.klen = KL;
+        }
         ACE_TRY(launch_gemm_nt(p, w.bg));
+        if (S > 1) {
+          const size_t total = (size_t)cnt * len;
+          splitk_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, w.bg>>>(part, S, len, total, w.Bf);
+          ACE_CUDA(cudaGetLastError());
+        }
         GemmNT r{};
         r.A = blkptr(w, j0, j0); r.lda = w.ld; r.a_tri = 2; r.Adiag = w.DX + (size_t)j0 * TB * TB;
         r.B = w.Bf; r.ldb = pw;
