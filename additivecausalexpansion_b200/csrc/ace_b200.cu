@@ -340,6 +340,15 @@ struct Core {
           shard_events.push_back(e);
         }
         shard_potrf = true;
+        // Inverse grown behind the panels (incremental) vs. split merge tree after the factorisation: the first
+        // wins while the Cholesky is bound by its serial panel chain (~0.85 ms per panel), i.e. while the GPUs have
+        // idle time to fill (C3: 47.3 -> 42.6 ms on 8 GPUs); when the trailing updates dominate, background work
+        // only competes with them (C4, n = 65536, 8 GPUs: 1.20 s split tree vs 1.25 s incremental).
+        {
+          const double nn = (double)n_pad;
+          const double chain_s = NP * 0.85e-3, update_s = nn * nn * nn / (3.0 * shard_world * 3.5e13);
+          shard_incr = 2.0 * chain_s >= update_s;
+        }
         if (const char* si = std::getenv("ACE_SHARD_INCR")) shard_incr = std::atoi(si) != 0;
       }
     }
@@ -944,9 +953,9 @@ int ace_fit_shard(ace_fit* f, const char* id128, int rank, int world) {
     ACE_CUDA(cudaStreamSynchronize(c.st));
     ACE_NCCL(nc.CommInitRank(&f->comm2, world, id2, rank));
   }
-  ACE_TRY(c.alloc_shard());
   c.shard_rank = rank;
   c.shard_world = world;
+  ACE_TRY(c.alloc_shard());
   if (f->gexec) {  // a graph captured before sharding is stale
     cudaGraphExecDestroy(f->gexec);
     cudaGraphDestroy(f->graph);
@@ -966,10 +975,10 @@ int ace_fit_shard_emulate(ace_fit* f, int world) {
     set_error("sharding needs ceil(n/128)*128 divisible by 128*world");
     return ACE_ERR_UNSUPPORTED;
   }
-  ACE_TRY(c.alloc_shard());
   c.shard_rank = 0;
   c.shard_world = world;
   c.shard_emulate = true;
+  ACE_TRY(c.alloc_shard());
   if (f->gexec) {
     cudaGraphExecDestroy(f->gexec);
     cudaGraphDestroy(f->graph);
