@@ -668,7 +668,6 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
     ACE_TRY(uut_inverse(w));
     if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));
     ACE_TRY(c.enqueue_alpha(c.Bf.p, 1));
-    c.kinv_partial = false;
   } else {
     // redundant Cholesky (ms[1]), then the split triangular inverse (ms[2]) and this rank's tiles of U U^T (ms[3])
     const ShardCtx cx = c.shard_ctx(f->comm, f->comm2);
@@ -687,7 +686,6 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
     ACE_TRY(uut_inverse_sharded(w, cx));
     if (timed) ACE_CUDA(cudaEventRecord(c.tev[4], c.st));
     ACE_TRY(c.enqueue_alpha_tri(c.A.p, 1));
-    c.kinv_partial = !c.shard_emulate;  // an emulated run leaves the complete inverse behind
   }
   if (!sharded) {
     ACE_TRY(c.enqueue_grad(c.Bf.p));
@@ -704,7 +702,6 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
   }
   ACE_TRY(c.enqueue_finalize(c.Bf.p, f->cfg, 1, sharded, sdense ? c.kdg.p : nullptr));
   if (timed) ACE_CUDA(cudaEventRecord(c.tev[5], c.st));
-  c.u_valid = true;
   return 0;
 }
 
@@ -787,7 +784,9 @@ int ace_fit_para_update(ace_fit* f, int iter, double* stats, double* gnorm) {
     ACE_CUDA(cudaMemcpyAsync(c.sc.p + SC_ITER, c.h_sc + SC_COUNT + 1, sizeof(double), cudaMemcpyHostToDevice, c.st));
     f->iter_dev = (double)iter;
   }
-  if (f->cfg.use_graph) {
+  // a fit sharded over real ranks launches eagerly: its iteration contains NCCL collectives on several streams
+  const bool use_graph = f->cfg.use_graph && !(c.shard_world > 1 && !c.shard_emulate);
+  if (use_graph) {
     if (!f->gexec) {
       ACE_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeThreadLocal));
       int s = enqueue_iteration(f, false);
@@ -809,12 +808,16 @@ int ace_fit_para_update(ace_fit* f, int iter, double* stats, double* gnorm) {
     ACE_TRY(enqueue_iteration(f, true));
     ACE_CUDA(cudaEventRecord(c.tev[7], c.st));
   }
+  // state of the buffers after this iteration (set here, not while enqueueing: a captured graph is replayed
+  // without re-running the enqueue code, and counting launches captures without executing)
+  c.u_valid = true;  // A / DX / DU hold the factor of the stored inverse
+  c.kinv_partial = c.shard_world > 1 && c.shard_dense && !c.shard_emulate;  // only this rank's tiles of K^-1 in Bf
   ACE_TRY(c.fetch_scalars());
   f->iter_dev = c.h_sc[SC_ITER];
   float t = 0;
   ACE_CUDA(cudaEventElapsedTime(&t, c.tev[6], c.tev[7]));
   f->ms[5] = t;
-  if (!f->cfg.use_graph) {
+  if (!use_graph) {
     for (int k = 0; k < 5; ++k) {
       ACE_CUDA(cudaEventElapsedTime(&t, c.tev[k], c.tev[k + 1]));
       f->ms[k] = t;
