@@ -1,8 +1,12 @@
-// shard_dense.cuh -- the dense part of ONE fit spread over the G GPUs of a node (first step).
+// shard_dense.cuh -- the dense part of ONE fit spread over the G GPUs of a node.
 //
-// After the (still redundant) Cholesky every rank holds L.  The two n^3/3 phases that follow are sharded:
+// All three n^3/3 phases are sharded; every rank ends with the complete factor L, U = L^-T, X = L^-1:
 //
-//  * triangular inverse: the bottom-up merge tree of chol.cuh is kept; its LOW levels (small nodes, ~6 % of the
+//  * triangular inverse, default while the panel chain bounds the Cholesky (potrf_sharded + gather_inverse_sharded):
+//    block row J of X for a column panel c only needs X[c0:j0, c], i.e. the rank's OWN columns, so every rank grows
+//    X[:, its panels] behind the panels on a background stream (batched split-K merges) with no exchange; one padded
+//    ncclAllGather at the end distributes the column panels.
+//  * triangular inverse, otherwise (trtri_merge_sharded): the bottom-up merge tree of chol.cuh is kept; its LOW levels (small nodes, ~6 % of the
 //    flops) run redundantly on every rank, the HIGH levels are split.  For a node with children [a,c), [c,b) the
 //    rows of U12 = (X21)^T = -(U11 L21^T) X22^T are independent, so the h*128 rows are cut into 2G slices and
 //    rank r computes slices r and 2G-1-r (U11 is triangular: the pairing balances the k-ranges exactly).  The
@@ -515,9 +519,9 @@ inline int trtri_merge_sharded(const DenseWork& w, const ShardCtx& cx) {
     if (level_is_split(cx, h))
       ACE_TRY(trtri_level_sharded(w, 0, w.nb, h, w.main, w.Bf, cx, /*need_lower=*/true));  // X complete: posterior in factor form
     else {
-      for (int k = 0; k < 1; ++k) shard_trace().level_mark(-h, 0, w.main);
+      shard_trace().level_mark(-h, 0, w.main);
       ACE_TRY(trtri_level(w, 0, w.nb, h, w.main, w.Bf));
-      for (int k = 1; k < 5; ++k) shard_trace().level_mark(-h, k, w.main);
+      for (int k = 1; k < 5; ++k) shard_trace().level_mark(-h, k, w.main);  // one phase only: the rest reads +0
     }
   }
   return 0;
