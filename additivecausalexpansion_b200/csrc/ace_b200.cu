@@ -1207,7 +1207,9 @@ int ace_fit_predict(ace_fit* f, const double* X2, const double* Z2, int nx, doub
   const int G = split ? c.shard_world : 1, r = split ? c.shard_rank : 0;
   const int chunk = round_up((nx + G - 1) / G, TB);  // rows per rank, on the 128 grid
   const int nx_all = chunk * G;                       // padded length of the gathered vectors
-  const int lo = std::min(nx, r * chunk), cnt = std::min(nx, lo + chunk) - lo;
+  // lo stays on the 128 grid (16-byte aligned TMA sources) and inside the nx_all-sized buffers even when this
+  // rank's block lies entirely beyond nx: such a rank computes cnt = 0 rows of zero-padded inputs
+  const int lo = r * chunk, cnt = std::max(0, std::min(nx, lo + chunk) - lo);
   DBuf<double> dX2, dZ2, dLZ2, Kx, kd, res;
   ACE_TRY(dX2.alloc((size_t)nx_all * c.p));
   ACE_TRY(dZ2.alloc((size_t)nx_all * c.Bz));

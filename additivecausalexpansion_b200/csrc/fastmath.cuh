@@ -31,8 +31,10 @@ __constant__ double kExpC[16] = {
     6755399441055744.0,           // 1.5 * 2^52
     0.0};
 
-// exp(x) for x <= ~700.  Arguments below -700 are clamped (result < 1e-304, i.e. 0 for our purposes);
-// NaN propagates (the comparison is false for NaN and the final step is a multiplication).
+// exp(x).  Arguments below -700 are clamped (result < 1e-304, i.e. 0 for our purposes); above 709.4 (2^n would need n = 1024) the
+// result is +inf like the reference's std::exp beyond 709.78 (a diverged run must surface as "gradients are not finite",
+// R/optimizer_classes.R:26-29, not as a silently zeroed kernel term); NaN propagates (the comparisons are false
+// for NaN and the final step is a multiplication).
 __device__ __forceinline__ double fast_exp(double x0) {
   const double x = (x0 < -700.0) ? -700.0 : x0;
   double t = fma(x, kExpC[13], kExpC[14]);  // round(x / ln2) via the 1.5 * 2^52 trick
@@ -45,7 +47,8 @@ __device__ __forceinline__ double fast_exp(double x0) {
   for (int k = 1; k <= 10; ++k) p = fma(p, r, kExpC[k]);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return p * __hiloint2double((n + 1023) << 20, 0);  // * 2^n, n in [-1010, 1010]
+  const double v = p * __hiloint2double((n + 1023) << 20, 0);  // * 2^n, n in [-1010, 1023]
+  return (x0 > 709.4) ? __longlong_as_double(0x7ff0000000000000LL) : v;
 }
 
 // 1/x for normal x (|x| in [1e-300, 1e300]): MUFU seed (~2^-23) + cubic step + quadratic step -> ~1 ulp

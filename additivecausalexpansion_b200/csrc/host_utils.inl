@@ -23,7 +23,9 @@ static int ncs_design(const double* x, int n, const double* knots_in, int nknots
   std::vector<double> dk((size_t)n * K);
   auto tp = [&](double xv, double c) {
     const double ind = (xv > c) ? 1.0 : 0.0, t = xv - c;
-    return deriv ? 3 * ind * (t * t) : ind * (t * t * t);
+    // arma::pow(x - k, 3) / arma::pow(x - k, 2) (src/ncs_basis_cpp.cpp:15-17,44-46) are element-wise std::pow calls in
+    // Armadillo (eop_aux::pow); t * t * t would round twice and differ by 1 ulp in a sizeable fraction of inputs
+    return deriv ? 3 * ind * std::pow(t, 2.0) : ind * std::pow(t, 3.0);
   };
   for (int r = 0; r < n; ++r) dk[r + (size_t)n * (K - 1)] = tp(x[r], kn[K - 1]);
   for (int i = 0; i < K - 1; ++i)

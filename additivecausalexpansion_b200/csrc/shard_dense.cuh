@@ -24,8 +24,10 @@
 //    critical path, so that all ranks end up with the complete L.  No rank ever needs K columns it does not own:
 //    the kernel build is sharded the same way and its exchange disappears.
 //
-// `emulate`: a single process plays all G ranks one after the other on one GPU (no NCCL).  Numerically this is
-// the multi-GPU path bit for bit, which lets the single-GPU test tier cover it.
+// `emulate`: a single process plays all G ranks one after the other on one GPU (no NCCL): the same world-strided
+// batched launches, tile subsets and packed buffers a real rank uses, with the exchanges replaced by the shared
+// memory of the one device (so the collectives themselves, and the cross-stream ordering around them, are only
+// exercised by the real 2-rank test, tests/test_gpu_shard.py).  Lets the single-GPU test tier cover the indexing.
 #pragma once
 #include <cstdio>
 #include "chol.cuh"
@@ -256,11 +258,12 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     // as two batched GEMMs over the owned panels (Wt_c = U[c rows, c0:j0] * L[J, c0:j0]^T; X[J,c] = -X_JJ Wt_c^T,
     // with the transposed copy U[c rows, J]).  A rank only ever needs its own columns of X: no exchange until the end.
     if (cx.incr && J >= 1 && w.bg) {
-      const int Gs = cx.emulate ? 1 : cx.world;
-      const int cf = cx.emulate ? 0 : cx.rank;
-      const int cnt = (cf < J) ? (J - cf + Gs - 1) / Gs : 0;
+      // emulation plays every rank in turn with the SAME world-strided batches a real rank launches
+      const int Gs = cx.world;
       ACE_CUDA(cudaStreamWaitEvent(w.bg, ev_copy[J], 0));  // block row J of L and X_JJ are in A (copies are in order)
-      if (cnt > 0) {
+      for (int cf = cx.emulate ? 0 : cx.rank; cf < (cx.emulate ? cx.world : cx.rank + 1); ++cf) {
+        const int cnt = (cf < J) ? (J - cf + Gs - 1) / Gs : 0;
+        if (cnt <= 0) continue;
         const long pw = (long)pb * TB, step = (long)Gs * pw;
         // few tiles (32 per problem) with a K range that grows to n: split K into chunks of <= 2048 so that the
         // background work is spread over the SMs instead of running as a handful of millisecond-long tiles
@@ -300,12 +303,11 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     tr.mark(J, 7, w.main);
     bool first = true;
     {
-      // my panels c >= J+2: the soonest needed one alone (its completion releases the look-ahead), all other
+      // a rank's panels c >= J+2: the soonest needed one alone (its completion releases the look-ahead), all its other
       // full-width ones in ONE batched launch of shrinking height (one tail instead of one per panel), a ragged
-      // last panel alone
-      const int G = cx.emulate ? 1 : cx.world;
-      int cf = J + 2;
-      while (cf < NP && !cx.mine(cf)) ++cf;
+      // last panel alone.  Emulation plays the ranks in turn, the owner of panel J+2 first, each with exactly the
+      // world-strided launches of a real rank.
+      const int G = cx.world;
       auto apply = [&](int c, int count) -> int {
         const int c0 = c * pb, c1 = std::min(c0 + pb, nb);
         const double* pan = Wp + (size_t)(c0 - j2) * TB;
@@ -318,10 +320,17 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
         }
         return launch_gemm_nt(g, w.main);
       };
-      if (cf < NP) {
+      const int nplay = cx.emulate ? G : 1;
+      for (int k = 0; k < nplay; ++k) {
+        const int r = cx.emulate ? (J + 2 + k) % G : cx.rank;
+        int cf = J + 2;
+        while (cf < NP && cf % G != r) ++cf;
+        if (cf >= NP) continue;
         ACE_TRY(apply(cf, 1));
-        ACE_CUDA(cudaEventRecord(ev_first[J], w.main));
-        first = false;
+        if (first) {
+          ACE_CUDA(cudaEventRecord(ev_first[J], w.main));
+          first = false;
+        }
         int cnt = 0, last_ragged = -1;
         for (int c = cf + G; c < NP; c += G) {
           if ((c + 1) * pb > nb) last_ragged = c; else ++cnt;

@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import api
-from ._lib import NotFiniteError
+from ._lib import AceError, NotFiniteError
 from .basis import set_basis
 from .fit import AceFit
 
@@ -138,13 +138,31 @@ class _KernelClass:
         return invKmatList
 
     # ---- the hot path: fused, device resident -----------------------------------------------------
+    @staticmethod
+    def _optim_key(Optim):
+        return (Optim.name, Optim.lr, Optim.beta1, Optim.beta2, Optim.momentum, bool(Optim.norm_clip), Optim.clip_at)
+
     def _handle(self, y, X, Z, Optim):
+        """The device-resident state behind this kernel object.  The reference uses the y, X, Z and Optim arguments
+        of EVERY call; here they are captured when the handle is created, so later calls are checked against them:
+        other data objects of the same shape are uploaded again, anything else (other shapes, other optimiser
+        settings) is refused instead of being silently ignored."""
         key = (id(y), id(X), id(Z))
         if self._fit is None:
             self._fit = AceFit(y, X, Z, self._par, kernel=self.kind, optimizer=Optim.name,
                                learning_rate=Optim.lr, beta1=Optim.beta1, beta2=Optim.beta2,
                                momentum=Optim.momentum, norm_clip=Optim.norm_clip, clip_at=Optim.clip_at,
                                std_y=self.stdy, device=self._device, use_graph=self._use_graph)
+            self._data_id, self._optim_id = key, self._optim_key(Optim)
+            return self._fit
+        if self._optim_key(Optim) != self._optim_id:
+            raise ValueError("para_update: the optimiser settings differ from the ones this kernel's device handle was "
+                             "created with; close() the kernel (or make a new one) to change them")
+        if key != self._data_id:
+            if np.shape(X) != (self._fit.n, self._fit.p) or np.size(y) != self._fit.n or \
+                    np.asarray(Z).reshape(self._fit.n, -1).shape[1] != self._fit.Bz:
+                raise ValueError("para_update: y, X, Z changed shape after the device handle was created")
+            self._fit.upload_data(y, X, Z)
             self._data_id = key
         return self._fit
 
@@ -159,6 +177,13 @@ class _KernelClass:
             stats, gnorm = fit.para_update(iter)
         except NotFiniteError as e:
             raise FloatingPointError(_NOT_FINITE) from e
+        except AceError as e:
+            # a non-positive pivot (status = its 1-based index): the reference's eigendecomposition route yields
+            # NaNs there and carries on until the optimiser stops with this very message (quirk Q10,
+            # src/kernel_SE_cpp.cpp:144-152 -> R/optimizer_classes.R:26-29)
+            if e.status > 0:
+                raise FloatingPointError(_NOT_FINITE) from e
+            raise
         if (iter % printevery == 0) and verbose:
             par = fit.parameters
             print("%5d | log Evidence %9.4f | RMSE %9.4f | Norm. noise var: %3.4f | Gradient L2: %3.4f"

@@ -714,7 +714,9 @@ void ace_oracle_ncs_basis(const double* x, int n_, const double* knots_in, int K
   const std::vector<double> knots = unique_sorted(knots_in, Kin);
   const size_t n = n_, K = knots.size();
   std::vector<double> d(n * K);
-  auto cube = [](double v) { return v * v * v; };
+  // arma::pow(x - k, 3) is evaluated element by element with std::pow (Armadillo's eop_aux::pow); v * v * v rounds
+  // twice and differs from it by 1 ulp for a sizeable fraction of inputs
+  auto cube = [](double v) { return std::pow(v, 3.0); };
   for (size_t r = 0; r < n; r++)  // :15
     d[r + n * (K - 1)] = (x[r] > knots[K - 1] ? 1.0 : 0.0) * cube(x[r] - knots[K - 1]);
   for (size_t i = 0; i + 1 < K; i++) {  // :16-19
@@ -735,7 +737,7 @@ void ace_oracle_ncs_basis_deriv(const double* x, int n_, const double* knots_in,
   const std::vector<double> knots = unique_sorted(knots_in, Kin);
   const size_t n = n_, K = knots.size();
   std::vector<double> d(n * K);
-  auto sq = [](double v) { return v * v; };
+  auto sq = [](double v) { return std::pow(v, 2.0); };  // arma::pow(x - k, 2), as above
   for (size_t r = 0; r < n; r++)  // :44
     d[r + n * (K - 1)] = 3 * (x[r] > knots[K - 1] ? 1.0 : 0.0) * sq(x[r] - knots[K - 1]);
   for (size_t i = 0; i + 1 < K; i++) {  // :45-48

@@ -36,6 +36,9 @@ with AceFit(prob.y, prob.X, prob.Z, prob.parameters, kernel=prob.kernel, std_y=p
     torch.cuda.synchronize(); dist.barrier()
     import time as _t
     t0 = _t.time(); pred_sh = f.predict(X2, tb["B"], prob.mean_y, prob.std_y); t_pred_sh = _t.time() - t0
+    # few, odd-numbered test points: some ranks receive an empty (or 8-byte-misaligned, before the fix) block
+    nx_s = 37
+    pred_sh_small = f.predict(X2[:nx_s].copy(order="F"), tb["B"][:nx_s].copy(order="F"), prob.mean_y, prob.std_y)
     if os.environ.get("ACE_SHARD_TRACE") and rank in (0, 1):
         from additivecausalexpansion_b200._lib import lib
         lib().ace_dbg_shard_trace_dump(rank)
@@ -62,6 +65,9 @@ if rank == 0:
         out["predict"] = {"nx": nx, "map_rel": float(np.abs(pred_sh["map"] - pred_1["map"]).max() / np.abs(pred_1["map"]).max()),
                           "var_rel": float(np.abs(pred_sh["var"] - pred_1["var"]).max() / np.abs(pred_1["var"]).max()),
                           "wall_s_sharded": t_pred_sh, "wall_s_single": t_pred_1}
+        pred_1s = g.predict(X2[:nx_s].copy(order="F"), tb["B"][:nx_s].copy(order="F"), prob.mean_y, prob.std_y)
+        out["predict_small_odd"] = {"nx": nx_s, "map_rel": float(np.abs(pred_sh_small["map"] - pred_1s["map"]).max() / np.abs(pred_1s["map"]).max()),
+                                    "var_rel": float(np.abs(pred_sh_small["var"] - pred_1s["var"]).max() / np.abs(pred_1s["var"]).max())}
         out.update({"ms_per_iter_sharded": ms_sh, "ms_per_iter_single": ms_1, "speedup": ms_1 / ms_sh, "phases_sharded": ph, "phases_single": g.last_timing_ms})
     print(json.dumps(out, default=float))
     json.dump(out, open(f"/root/repo/gpurun_out/shard_check_{cfg}_w{world}.json", "w"), indent=1, default=float)

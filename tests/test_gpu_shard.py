@@ -26,3 +26,5 @@ def test_sharded_fit_matches_single_gpu():
     for it in res["iters"]:
         assert it["evid_rel"] <= 1e-12 and it["grad_rel"] <= 1e-9 and it["par_abs"] <= 1e-10
     assert res["predict"]["map_rel"] <= 1e-9 and res["predict"]["var_rel"] <= 1e-8
+    # nx = 37 over 2 ranks: rank 1's block starts beyond nx (misaligned TMA source / hang)
+    assert res["predict_small_odd"]["map_rel"] <= 1e-9 and res["predict_small_odd"]["var_rel"] <= 1e-8
