@@ -99,6 +99,9 @@ SIGNATURES = {
     "ace_fit_predict_marginal": (_i, [_vp, _p, _p, _p, _i, _d, _d, _d, _i, _p, _p, _p, _p]),
     "ace_dbg_gemm_nt": (_i, [_p, _p, _p, _i, _i, _i, _d, _d, _i]),
     "ace_dbg_spd_inverse": (_i, [_p, _i, _p, _p, _p, _p]),
+    "ace_dbg_spd_inverse_fused": (_i, [_p, _i, _p, _p]),
+    "ace_dbg_diag_block": (_i, [_p, _i, _p, _p, _p, _p]),
+    "ace_dbg_diag_block_timeline": (_i, [C.POINTER(C.c_longlong), _i]),
     "ace_bench_dense": (_i, [_i, _i, _p]),
     "ace_dbg_set_trtri_max_h": (_i, [_i]),
     "ace_dbg_trtri_raw": (_i, [_p, _i, _p, _p, _p, _p]),

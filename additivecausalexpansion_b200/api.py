@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import c_double_p, check, lib
+from ._lib import AceError, c_double_p, check, lib  # noqa: F401
 
 
 def _f(a, two_d=False):
@@ -249,6 +249,25 @@ def dbg_spd_inverse(A, want_L=True, want_inv=True):
     ms = np.zeros(3)
     check(lib().ace_dbg_spd_inverse(_p(A), n, _p(L), _p(inv), _p(d), _p(ms)), "dbg_spd_inverse")
     return {"L": L, "inv": inv, "diagL": d, "ms": ms}
+
+
+def dbg_spd_inverse_fused(A):
+    """The production schedule (fused diagonal-block kernel, fused panel TRSM, inverse behind the panels)."""
+    A = _f(A)
+    n = A.shape[0]
+    inv, d = np.empty((n, n), order="F"), np.empty(n)
+    check(lib().ace_dbg_spd_inverse_fused(_p(A), n, _p(inv), _p(d)), "dbg_spd_inverse_fused")
+    return {"inv": inv, "diagL": d}
+
+
+def dbg_diag_block(A):
+    """The fused diagonal-block kernel alone (n <= 512): X = L^-1, U = X', diag(L), diagonal 128-tiles of L."""
+    A = _f(A)
+    n = A.shape[0]
+    X, U, L = (np.empty((n, n), order="F") for _ in range(3))
+    d = np.empty(n)
+    check(lib().ace_dbg_diag_block(_p(A), n, _p(X), _p(U), _p(d), _p(L)), "dbg_diag_block")
+    return {"X": X, "U": U, "diagL": d, "Ldiag": L}
 
 
 def bench_dense(n, reps=1):

@@ -272,6 +272,7 @@ struct Core {
   cudaStream_t st = nullptr, side = nullptr, aux = nullptr, bgst = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   DBuf<double> Wp0, Wp1, Wsmall;  // fused panel TRSM workspaces (chol.cuh)
+  DBuf<double> diag_ws;           // scratch of the fused diagonal-block kernel (diag_block.cuh)
   int panel_blocks = 4;
   cudaEvent_t tev[8] = {};
   DBuf<double> X, Z, LZ, y, theta, m, v, grad, tab, sc, A, Bf, DX, DU, dvec, alpha, uvec, svec, Ka, pu, ps, partials;
@@ -432,11 +433,14 @@ struct Core {
       // The fused panel TRSM (early X_JJ) also enables the incremental inverse behind the panels (chol.cuh); together
       // they pay off at every size measured: C2 (n=4096) 8.65 -> 7.87 ms, C5 (n=8192) 27.0 -> 23.5 ms, C3 (n=16384)
       // 164.9 -> 158.3 ms per iteration.  ACE_FUSED_TRSM=0 switches both off.
-      const bool want = fu ? (std::atoi(fu) != 0) : (n_pad >= 1024);
+      const bool want = fu ? (std::atoi(fu) != 0) : true;
       if (pow2 && panel_blocks >= 2 && want) {
         ACE_TRY(Wp0.alloc(N * panel_blocks * TB));
         ACE_TRY(Wp1.alloc(N * panel_blocks * TB));
         ACE_TRY(Wsmall.alloc((size_t)(panel_blocks * TB / 2) * (panel_blocks * TB / 2)));
+        // one cluster launch per diagonal block instead of ~16 small launches (ACE_DIAG_FUSED=0: the leaf recursion)
+        const char* df = std::getenv("ACE_DIAG_FUSED");
+        if (!(df && std::atoi(df) == 0)) ACE_TRY(diag_ws.alloc(dg::ws_doubles(panel_blocks)));
       }
     }
     if (need_grad) {
@@ -478,6 +482,7 @@ struct Core {
     w.panel_blocks = panel_blocks;
     if (allow_fused && Wp0.p) {
       w.Wp[0] = Wp0.p; w.Wp[1] = Wp1.p; w.Wsmall = Wsmall.p; w.ev_copy[0] = ev[6]; w.ev_copy[1] = ev[7];
+      w.diag_ws = diag_ws.p;
     }
     w.A = Abuf; w.ld = n_pad; w.nb = n_pad / TB; w.DX = DX.p; w.DU = DU.p; w.dvec = dvec.p; w.info = info.p;
     w.Bf = Bbuf; w.main = st; w.side = side; w.aux = aux; w.bg = bgst; w.ev_half = ev[4]; w.ev_aux = ev[5];

@@ -484,6 +484,73 @@ int ace_dbg_spd_inverse(const double* A, int n, double* L, double* inv, double* 
   return 0;
 }
 
+// production schedule (fused diagonal-block kernel, fused panel TRSM, incremental inverse): inverse + diag(L)
+int ace_dbg_spd_inverse_fused(const double* A, int n, double* inv, double* diagL) {
+  if (!A || n < 1) return usage("spd_inverse_fused: bad argument");
+  Core c;
+  ACE_TRY(c.init(g_device, n, 1, 1, 0, true, false));
+  ACE_TRY(upload_matrix(c.A.p, c.n_pad, c.n_pad, A, n, n, c.st));
+  if (c.n_pad > n) pad_identity_kernel<<<(c.n_pad - n + 255) / 256, 256, 0, c.st>>>(c.A.p, c.n_pad, n, c.n_pad);
+  ACE_CUDA(cudaGetLastError());
+  DenseWork w = c.dense(c.A.p, c.Bf.p);
+  ACE_TRY(spd_inverse(w));
+  if (inv) ACE_TRY(download_matrix(inv, n, n, c.Bf.p, c.n_pad, c.st));
+  if (diagL) ACE_CUDA(cudaMemcpyAsync(diagL, c.dvec.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.st));
+  ACE_TRY(c.fetch_scalars());
+  if (c.h_info() > 0) return c.h_info();
+  return 0;
+}
+
+// the fused diagonal-block kernel alone on an n x n SPD matrix, n <= 128 * panel width: X = L^-1 assembled from its
+// output layout (DX tiles on the diagonal, lower 128-blocks of A elsewhere), U likewise, diag(L), and the diagonal
+// 128-tiles of L (the only part of L the layout keeps)
+// SM clock stamps of the kernel's phases (8 per tile column: T0..T4 by warp 0 of CTA 0, F0..F2 by the factoring warp;
+// then 4 per merge level and the end), 8 * (nt + 8) values; nt = 4 * ceil(n / 128) tile columns
+static long long* g_diag_dbg_host = nullptr;
+int ace_dbg_diag_block_timeline(long long* stamps, int count) {
+  if (!stamps || !g_diag_dbg_host) return usage("dbg_diag_block_timeline: run ace_dbg_diag_block first");
+  for (int i = 0; i < count && i < 8 * 40; ++i) stamps[i] = g_diag_dbg_host[i];
+  return 0;
+}
+
+int ace_dbg_diag_block(const double* A, int n, double* X, double* U, double* diagL, double* Ldiag_tiles) {
+  if (!A || n < 1) return usage("dbg_diag_block: bad argument");
+  Core c;
+  ACE_TRY(c.init(g_device, n, 1, 1, 0, true, false));
+  if (c.n_pad / TB > c.panel_blocks || !c.diag_ws.p) return usage("dbg_diag_block: n exceeds one diagonal block");
+  ACE_TRY(upload_matrix(c.A.p, c.n_pad, c.n_pad, A, n, n, c.st));
+  if (c.n_pad > n) pad_identity_kernel<<<(c.n_pad - n + 255) / 256, 256, 0, c.st>>>(c.A.p, c.n_pad, n, c.n_pad);
+  ACE_CUDA(cudaGetLastError());
+  ACE_CUDA(cudaMemsetAsync(c.info.p, 0, sizeof(int), c.st));
+  DenseWork w = c.dense(c.A.p, c.Bf.p);
+  DBuf<long long> dbg;
+  ACE_TRY(dbg.alloc(8 * 40));
+  ACE_CUDA(cudaMemsetAsync(dbg.p, 0, sizeof(long long) * 8 * 40, c.st));
+  w.diag_dbg = dbg.p;
+  ACE_TRY(diag_block_factor_invert(w, 0, c.n_pad / TB, c.st));
+  ACE_TRY(c.fetch_scalars());
+  if (!g_diag_dbg_host) g_diag_dbg_host = new long long[8 * 40];
+  ACE_CUDA(cudaMemcpy(g_diag_dbg_host, dbg.p, sizeof(long long) * 8 * 40, cudaMemcpyDeviceToHost));
+  const size_t N = c.n_pad;
+  std::vector<double> hA(N * N), hDX(N * TB), hDU(N * TB), hd(N);
+  ACE_CUDA(cudaMemcpy(hA.data(), c.A.p, sizeof(double) * N * N, cudaMemcpyDeviceToHost));
+  ACE_CUDA(cudaMemcpy(hDX.data(), c.DX.p, sizeof(double) * N * TB, cudaMemcpyDeviceToHost));
+  ACE_CUDA(cudaMemcpy(hDU.data(), c.DU.p, sizeof(double) * N * TB, cudaMemcpyDeviceToHost));
+  ACE_CUDA(cudaMemcpy(hd.data(), c.dvec.p, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      const int bi = i / TB, bj = j / TB;
+      const size_t t = (size_t)bi * TB * TB + (size_t)(j % TB) * TB + (i % TB);
+      const double a = hA[i + (size_t)j * N];
+      if (X) X[i + (size_t)j * n] = (bi == bj) ? hDX[t] : (bi > bj ? a : 0.0);
+      if (U) U[i + (size_t)j * n] = (bi == bj) ? hDU[t] : (bi < bj ? a : 0.0);
+      if (Ldiag_tiles) Ldiag_tiles[i + (size_t)j * n] = (bi == bj && i >= j) ? a : 0.0;
+    }
+  if (diagL) std::memcpy(diagL, hd.data(), sizeof(double) * n);
+  if (c.h_info() > 0) return c.h_info();
+  return 0;
+}
+
 int ace_dbg_set_trtri_max_h(int h) {
   dbg_trtri_max_h() = h;
   return 0;

@@ -17,6 +17,7 @@
 #pragma once
 #include "dgemm_nt.cuh"
 #include "fastmath.cuh"
+#include "diag_block.cuh"
 
 #include <cstdlib>
 #include <vector>
@@ -311,6 +312,10 @@ struct DenseWork {
   double* Wp[2] = {nullptr, nullptr};  // n_pad x (panel_blocks*128) each, ld = n_pad
   double* Wsmall = nullptr;            // (panel_blocks*128/2)^2 doubles: workspace of the early merges
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  // fused diagonal-block kernel (diag_block.cuh): scratch of dg::ws_doubles(panel_blocks) doubles; nullptr = the
+  // recursion of 128-wide leaf kernels + early merge levels (ACE_DIAG_FUSED=0)
+  double* diag_ws = nullptr;
+  long long* diag_dbg = nullptr;  // debug: phase clock stamps of the diagonal-block kernel
 };
 
 inline int configure_dense_kernels() {
@@ -320,6 +325,7 @@ inline int configure_dense_kernels() {
                                 (int)leaf::SMEM_BYTES));
   ACE_CUDA(cudaFuncSetAttribute(trsm_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)trsml::SMEM_BYTES));
+  ACE_TRY(configure_diag_kernel());
   return 0;
 }
 
@@ -364,13 +370,28 @@ inline int potrf_rec(const DenseWork& w, int a, int b, cudaStream_t st) {
   return potrf_rec(w, c, b, st);
 }
 
+inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws, int h_min = 1);
+
+// Diagonal block [j0, j1) of the panel schedule: L_JJ, X_JJ = L_JJ^-1 (lower 128-blocks), U_JJ (upper), DX / DU tiles,
+// dvec.  One cluster launch (diag_block.cuh), or the leaf recursion followed by the early merge levels.
+inline int diag_block_factor_invert(const DenseWork& w, int j0, int j1, cudaStream_t st) {
+  if (w.diag_ws != nullptr) {
+    DiagArgs a{};
+    a.A = w.A; a.ld = w.ld; a.blk0 = j0; a.nblk = j1 - j0; a.DX = w.DX; a.DU = w.DU; a.dvec = w.dvec; a.info = w.info;
+    a.S = w.diag_ws;
+    a.W = w.diag_ws + (size_t)w.panel_blocks * TB * w.panel_blocks * TB;
+    a.dbg = w.diag_dbg;
+    return launch_diag_block(a, st);
+  }
+  ACE_TRY(potrf_rec(w, j0, j1, st));
+  return trtri_merge_range(w, j0, j1, st, w.Wsmall);
+}
+
 // Phase 1: right-looking blocked Cholesky with one-panel look-ahead on two streams.
 //   panel(J)  : factor the diagonal block + TRSM of the rows below it        (side stream)
 //   upd_a(J)  : trailing update restricted to the next panel's block column  (main stream)
 //   upd_b(J)  : the rest of the trailing update                              (main stream)
 // panel(J+1) only waits for upd_a(J), so it overlaps upd_b(J).
-inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st, double* ws, int h_min = 1);
-
 // fork_at > 0: as soon as the leading fork_at block rows/columns of L are final, their triangular inverse is
 // started on the aux stream (it only touches A[0:fork_at, 0:fork_at], which potrf never reads again); the
 // caller joins on ev_aux.  The tail of a Cholesky is latency bound (a chain of 128-wide leaf kernels with
@@ -394,13 +415,13 @@ inline int potrf_blocked(const DenseWork& w, int fork_at = 0, int fork_when = 0,
       v->push_back(e);
     };
     mark(w.trace ? &w.trace->panel_begin : nullptr, w.side);
-    ACE_TRY(potrf_rec(w, j0, j1, w.side));
     const bool fused = (w.Wp[0] != nullptr);
     const double* panel = blkptr(w, j1 < nb ? j1 : j0, j0);  // operand of the trailing update
     if (!fused) {
+      ACE_TRY(potrf_rec(w, j0, j1, w.side));
       ACE_TRY(trsm_rec(w, j1, nb, j0, j1, w.side));
     } else {
-      ACE_TRY(trtri_merge_range(w, j0, j1, w.side, w.Wsmall));  // X_JJ (lower blocks of the diagonal block) + U_JJ
+      ACE_TRY(diag_block_factor_invert(w, j0, j1, w.side));  // L_JJ, X_JJ (lower blocks of the diagonal block), U_JJ
       if (j1 < nb) {
         if (J >= 2) ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_copy[J & 1], 0));  // Wp[J&1] free again
         GemmNT t{};

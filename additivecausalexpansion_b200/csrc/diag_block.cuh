@@ -1,0 +1,480 @@
+// diag_block.cuh -- Cholesky factor AND triangular inverse of one diagonal block (<= 512 x 512) of the blocked
+// factorisation in ONE launch: a thread-block cluster of 8 CTAs.
+//
+// Why: the diagonal blocks are the serial chain of the right-looking Cholesky (chol.cuh).  Done as a recursion
+// of 128-wide leaf kernels (4 x potrf_leaf + 4 x trsm_leaf + 8 small GEMM launches, ~0.6 ms per 512-block:
+// profiles/r01) the chain bounds the tail of the factorisation on one GPU, all of C2 (n = 4096) and the sharded
+// fit.  Here the block is cut into 32 x 32 tiles and processed by the 64 warps of the cluster:
+//
+//   factor   right-looking over the 16 tile columns:  one warp factors the diagonal tile in registers
+//            (column broadcast through shared memory, MUFU-seeded rsqrt) and inverts it;  every warp then solves
+//            tiles of the column as a product with that inverse (DMMA) and updates trailing tiles (DMMA).  The warp
+//            that factors tile k+1 updates it first and factors it while the others finish the trailing update
+//            of step k (look-ahead): two cluster barriers per tile column.
+//   inverse  X = L^-1 by bottom-up pairwise merging on the 32-tile grid (X21 = -X22 L21 X11 as two NT products,
+//            exactly the scheme of trtri_level in chol.cuh one level further down), two barriers per level.
+//   output   the layout the rest of the dense engine expects from potrf_rec + trtri_merge_range: L in the
+//            diagonal 128-tiles of A, X / U in the off-diagonal 128-blocks of the block (lower / upper), dense
+//            DX / DU tiles, diag(L) in dvec, the first non-positive pivot in info.
+//
+// All exchange between CTAs goes through global memory (the 2 MB block stays in L2) ordered by
+// barrier.cluster (release / acquire at cluster scope); operands reach the tensor pipe through a warp-private
+// shared-memory stage filled by TMA bulk copies (cp.async.bulk, L2 -> smem) on a per-warp mbarrier.  Replaces the eigendecomposition
+// route of invkernel_cpp for the diagonal blocks (src/kernel_SE_cpp.cpp:137-157).
+#pragma once
+#include "common.cuh"
+#include "fastmath.cuh"
+
+namespace ace {
+
+struct DiagArgs {
+  double* A;       // matrix base (column-major, ld)
+  long ld;
+  int blk0, nblk;  // first 128-block on the diagonal, number of 128-blocks (<= 4 by default)
+  double* DX;      // dense diagonal tiles of X = L^-1 (lower), tile t at + t * 128 * 128
+  double* DU;      // dense diagonal tiles of U = L^-T (upper)
+  double* dvec;    // diag(L)
+  int* info;       // 0, or 1-based global index of the first non-positive pivot
+  double* S;       // scratch (nblk*128)^2: X below / U above the diagonal while the inverse is built
+  double* W;       // scratch (nblk*128/2)^2: the W^T = U11 L21^T products of one merge level
+  long long* dbg;  // optional (debug): SM clock stamps of the phases, see ace_dbg_diag_block_timeline
+};
+
+namespace dg {
+constexpr int TS = 32;                    // tile edge
+constexpr int NC = 8;                     // CTAs per cluster (portable maximum)
+constexpr int WARPS = 8, THREADS = WARPS * 32;
+constexpr int GW = NC * WARPS;            // warps in the cluster
+constexpr int LDT = 36;                   // stride of a staged tile: rows 16-byte aligned, DMMA fragment loads conflict free
+constexpr int STAGE = 2 * TS * LDT + 2;   // doubles per warp: one A tile + one B tile + (mbarrier, its phase)
+constexpr size_t SMEM_BYTES = (size_t)WARPS * STAGE * 8;
+constexpr uint32_t TILE_PAIR_BYTES = 2 * TS * TS * 8;
+constexpr int KEEP_ALL = 0, KEEP_UPPER = 1, KEEP_LOWER = 2;
+inline size_t ws_doubles(int panel_blocks) {
+  const size_t N = (size_t)panel_blocks * 128;
+  return N * N + (N / 2) * (N / 2);
+}
+}  // namespace dg
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// all threads of all CTAs of the cluster; orders global (and shared) memory accesses at cluster scope
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Two 32 x 32 tiles (column c at src + c * ld) -> the warp's stage (column c at dst + c * LDT): lane c moves column c
+// of both with one TMA bulk copy each (256 B), completion on the warp's own mbarrier.
+__device__ __forceinline__ void dg_stage_pair(double* stage, const double* A, long lda, const double* B, long ldb,
+                                              int lane) {
+  using namespace dg;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * TS * LDT);
+  uint32_t* ph = reinterpret_cast<uint32_t*>(bar + 1);
+  const uint32_t phase = *ph;
+  fence_proxy_async();  // the stage doubles as scratch of the tile factorisation (generic-proxy accesses)
+  if (lane == 0) mbar_arrive_expect_tx(bar, TILE_PAIR_BYTES);
+  __syncwarp();
+  tma_bulk_g2s(stage + lane * LDT, A + (size_t)lane * lda, TS * 8, bar);
+  tma_bulk_g2s(stage + TS * LDT + lane * LDT, B + (size_t)lane * ldb, TS * 8, bar);
+  mbar_wait(bar, phase);
+  __syncwarp();
+  if (lane == 0) *ph = phase ^ 1u;
+}
+
+// One warp:  C = beta * C + alpha * sum_{t < nk} A_t B_t^T  on 32 x 32 tiles (A_t at A + t * sa, B_t at B + t * sb),
+// optional transposed copy Ct.  Tile ma_t of the A sequence / mb_t of the B sequence is triangular and stored with
+// the other triangle occupied by something else: only its upper (KEEP_UPPER: row <= col) or lower part is used.
+// C may alias A_0 when nk == 1 (the operands are staged completely before anything is stored).
+__device__ __noinline__ void dg_tile_gemm(double* stage, int lane, const double* A, long lda, long sa, int ma_t,
+                                             int ma_kind, const double* B, long ldb, long sb, int mb_t, int mb_kind,
+                                             int nk, double alpha, double beta, double* C, long ldc, double* Ct,
+                                             long ldct) {
+  using namespace dg;
+  const int g = lane >> 2, tq = lane & 3;
+  double acc[4][4][2];
+  if (beta != 0.0) {  // acc = (beta / alpha) C, so that alpha * acc ends as beta C + alpha sum
+    const double sc = beta / alpha;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          acc[mt][nt][e] = sc * __ldcg(C + (mt * 8 + g) + (size_t)(nt * 8 + 2 * tq + e) * ldc);
+  } else {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  }
+  double* sA = stage;
+  double* sB = stage + TS * LDT;
+#pragma unroll 1
+  for (int t = 0; t < nk; ++t) {
+    __syncwarp();  // everybody is done reading the previous tiles (and has seen the phase word)
+    dg_stage_pair(stage, A + (size_t)t * sa, lda, B + (size_t)t * sb, ldb, lane);
+    const int ka = (t == ma_t) ? ma_kind : KEEP_ALL, kb = (t == mb_t) ? mb_kind : KEEP_ALL;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int k = ks * 4 + tq;
+      double a[4], b[4];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const int row = mt * 8 + g;
+        double v = sA[row + k * LDT];
+        if (ka == KEEP_UPPER) v = (row <= k) ? v : 0.0;
+        if (ka == KEEP_LOWER) v = (row >= k) ? v : 0.0;
+        a[mt] = v;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int row = nt * 8 + g;
+        double v = sB[row + k * LDT];
+        if (kb == KEEP_UPPER) v = (row <= k) ? v : 0.0;
+        if (kb == KEEP_LOWER) v = (row >= k) ? v : 0.0;
+        b[nt] = v;
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const double v = alpha * acc[mt][nt][e];
+        acc[mt][nt][e] = v;
+        __stcg(C + (mt * 8 + g) + (size_t)(nt * 8 + 2 * tq + e) * ldc, v);
+      }
+  if (Ct != nullptr) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        __stcg(reinterpret_cast<double2*>(Ct + (nt * 8 + 2 * tq) + (size_t)(mt * 8 + g) * ldct),
+               make_double2(acc[mt][nt][0], acc[mt][nt][1]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp: Cholesky of a 32 x 32 diagonal tile and the inverse of its factor.
+// The tile lives in registers in a 2-D cyclic layout -- lane (ty, tx) = (lane / 8, lane % 8) owns the elements
+// (4a + ty, 8b + tx), a < 8, b < 4 -- so that "which column" is a lane predicate, not a register index: the column
+// loops are ROLLED (4 columns per template instance), the code stays a few KB (a fully unrolled row-per-lane
+// version was instruction-fetch bound: 12 us per tile), and all 32 lanes share the rank-1 updates.
+// ---------------------------------------------------------------------------------------------
+template <int JB, int H>
+__device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, double* colbuf, double* dg_, double* idg,
+                                             int tx, int ty, int* info, int gidx0) {
+  constexpr int A0 = 2 * JB + H;  // row block of the pivots of these 4 columns
+#pragma unroll 1
+  for (int jj = 0; jj < 4; ++jj) {
+    const int jx = 4 * H + jj, j = 8 * JB + jx;
+    double* cb = colbuf + (j & 1) * 32;
+    if (tx == jx) {
+#pragma unroll
+      for (int a = A0; a < 8; ++a) cb[4 * a + ty] = r[a][JB];
+    }
+    __syncwarp();
+    const double pj = cb[j];
+    // one MUFU-seeded reciprocal square root serves the whole column: 1/L_jj = y, L_jj = p y, 1/p = y^2
+    const double inv = fast_rsqrt(pj);
+    const double invp = inv * inv;
+    double lm[8], cm[4];
+#pragma unroll
+    for (int a = A0; a < 8; ++a) lm[a] = cb[4 * a + ty] * invp;
+#pragma unroll
+    for (int b = JB; b < 4; ++b) cm[b] = cb[8 * b + tx];
+    lm[A0] = (ty > jj) ? lm[A0] : 0.0;   // rows <= j (only block A0 straddles the pivot)
+    cm[JB] = (tx > jx) ? cm[JB] : 0.0;   // columns <= j (only block JB straddles it)
+#pragma unroll
+    for (int a = A0; a < 8; ++a)
+#pragma unroll
+      for (int b = JB; b < 4; ++b) r[a][b] = fma(-lm[a], cm[b], r[a][b]);  // entries above the diagonal: never read
+    // the column of L leaves AFTER the update was issued: it is off the critical path (the owners' copy of column j
+    // is untouched by the update: their cm[JB] is masked to zero)
+    if (tx == jx) {
+#pragma unroll
+      for (int a = A0; a < 8; ++a) {
+        const int i = 4 * a + ty;
+        if (i > j) Ls[i + j * 33] = r[a][JB] * inv;
+        if (i == j) {
+          double sq = pj * inv;
+          sq = fma(fma(-sq, sq, pj), 0.5 * inv, sq);
+          dg_[j] = sq;
+          idg[j] = inv;
+          if (!(pj > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
+        }
+      }
+    }
+  }
+}
+
+// rows j = 4 A .. 4 A + 3 of X = L^-1 (right-looking substitution on r = I): X(j, :) = r(j, :) / L_jj, then
+// r(i, :) -= L(i, j) X(j, :) for i > j.  X(j, k), k < j goes to the upper triangle of Ls as U(k, j).
+template <int A>
+__device__ __forceinline__ void dg_inv_rows(double (&r)[8][4], double* Ls, double* rowbuf, const double* idg, int tx,
+                                            int ty) {
+  constexpr int BMAX = A / 2;  // column blocks 0 .. BMAX hold the columns k <= j
+#pragma unroll 1
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = 4 * A + jj;
+    double* rb = rowbuf + (j & 1) * 32;
+    if (ty == jj) {
+      const double dj = idg[j];
+#pragma unroll
+      for (int b = 0; b <= BMAX; ++b) {
+        const int k = 8 * b + tx;
+        if (k <= j) {
+          const double x = r[A][b] * dj;
+          rb[k] = x;
+          if (k < j) Ls[k + j * 33] = x;
+        }
+      }
+    }
+    __syncwarp();
+    double lm[8], xm[4];
+#pragma unroll
+    for (int a = A; a < 8; ++a) lm[a] = Ls[4 * a + ty + j * 33];
+    lm[A] = (ty > jj) ? lm[A] : 0.0;
+#pragma unroll
+    for (int b = 0; b <= BMAX; ++b) xm[b] = rb[8 * b + tx];
+    xm[BMAX] = (tx <= 4 * (A % 2) + jj) ? xm[BMAX] : 0.0;  // columns > j of the straddling block
+#pragma unroll
+    for (int a = A; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b <= BMAX; ++b) r[a][b] = fma(-lm[a], xm[b], r[a][b]);
+  }
+}
+
+// Writes L (lower of At), diag(L) -> dv, X = L^-1 (lower) and U = X^T (upper) -> St (full 32 x 32 tile).
+__device__ __noinline__ void dg_factor_tile(double* sm, int lane, double* At, long ld, double* St, long lds,
+                                            double* dv, int* info, int gidx0) {
+  double* Ls = sm;                 // [32][33]: strictly lower = L, strictly upper = U (filled by the inverse)
+  double* colbuf = sm + 32 * 33;   // 2 x 32: pivot column / row, double buffered
+  double* dgl = colbuf + 64;       // L_jj
+  double* idg = dgl + 32;          // 1 / L_jj
+  const int tx = lane & 7, ty = lane >> 3;
+  double r[8][4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int a = 0; a < 8; ++a) r[a][b] = __ldcg(At + (4 * a + ty) + (size_t)(8 * b + tx) * ld);
+  dg_chol_cols<0, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<0, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<1, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<1, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<2, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<2, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<3, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<3, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  __syncwarp();
+  // L out: column c, lane = row (coalesced)
+#pragma unroll 4
+  for (int c = 0; c < 32; ++c) {
+    if (lane > c) __stcg(At + lane + (size_t)c * ld, Ls[lane + c * 33]);
+    if (lane == c) __stcg(At + lane + (size_t)c * ld, dgl[c]);
+  }
+  dv[lane] = dgl[lane];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r[a][b] = (4 * a + ty == 8 * b + tx) ? 1.0 : 0.0;
+  dg_inv_rows<0>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<1>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<2>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<3>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<4>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<5>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<6>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<7>(r, Ls, colbuf, idg, tx, ty);
+  __syncwarp();
+  // X (lower) / U (upper) tile out: column c, lane = row.  X(i, c) = U(c, i) = Ls[c + i * 33] for i > c.
+#pragma unroll 4
+  for (int c = 0; c < 32; ++c) {
+    const double v = (lane > c) ? Ls[c + lane * 33] : ((lane == c) ? idg[c] : Ls[lane + c * 33]);
+    __stcg(St + lane + (size_t)c * lds, v);
+  }
+  __syncwarp();
+}
+
+__global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2) diag_block_kernel(const DiagArgs a) {
+  using namespace dg;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  // warp index inside the cluster, CTA index fastest: consecutive tasks go to different SMs (a tile product is
+  // bound by the SM's FP64 tensor rate: eight of them on one SM take four times as long as two)
+  const int gw = warp * NC + crank;
+  double* stage = reinterpret_cast<double*>(smraw) + warp * STAGE;
+  if (lane == 0) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * TS * LDT);
+    mbar_init(bar, 1);
+    *reinterpret_cast<uint32_t*>(bar + 1) = 0u;
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int nt = a.nblk * 4;            // 32-tiles per side
+  const long N = (long)nt * TS;
+  const long ld = a.ld;
+  double* Ab = a.A + (size_t)a.blk0 * 128 * (ld + 1);
+  double* dv = a.dvec + (size_t)a.blk0 * 128;
+  auto At = [&](int i, int j) { return Ab + (size_t)i * TS + (size_t)j * TS * ld; };
+  auto St = [&](int i, int j) { return a.S + (size_t)i * TS + (size_t)j * TS * N; };
+  auto fw = [&](int k) { return k % NC; };  // the warp that factors diagonal tile k: warp 0 of CTA k mod NC
+  // debug stamps: T(k, s) by warp 0 of CTA 0 (s = 0..4: before B1, after B1, after its column solves, after B2, after
+  // its trailing tiles), F(k, s) by the factoring warp of tile k (0: start of its diagonal update, 1: after it, 2:
+  // after the factorisation); 8 slots per tile column, then 4 per merge level, then the end
+  auto stampT = [&](int k, int sidx) {
+    if (a.dbg != nullptr && gw == 0 && lane == 0) a.dbg[8 * k + sidx] = clock64();
+  };
+  auto stampF = [&](int k, int sidx) {
+    if (a.dbg != nullptr && lane == 0) a.dbg[8 * k + 5 + sidx] = clock64();
+  };
+
+  // ------------------------------------------------------------------ factorisation
+  if (gw == fw(0)) {
+    stampF(0, 1);
+    dg_factor_tile(stage, lane, At(0, 0), ld, St(0, 0), N, dv, a.info, a.blk0 * 128);
+    stampF(0, 2);
+  }
+#pragma unroll 1
+  for (int k = 0; k < nt; ++k) {
+    stampT(k, 0);
+    cluster_barrier();  // L_kk, X_kk visible; trailing update of step k-1 complete
+    stampT(k, 1);
+    // column k: L_ik = A_ik X_kk^T (in place)
+    for (int i = k + 1 + gw; i < nt; i += GW)
+      dg_tile_gemm(stage, lane, At(i, k), ld, 0, -1, KEEP_ALL, St(k, k), N, 0, 0, KEEP_LOWER, 1, 1.0, 0.0, At(i, k), ld,
+                   nullptr, 0);
+    stampT(k, 2);
+    cluster_barrier();  // column k of L visible
+    stampT(k, 3);
+    if (k + 1 >= nt) break;
+    // trailing update A_ij -= L_ik L_jk^T for k < j <= i.  The warp that factors tile k+1 takes (k+1, k+1) and goes on
+    // factoring (look-ahead); the other tiles, in column-major order, are dealt over the remaining warps.
+    const int f = fw(k + 1);
+    if (gw == f) {
+      stampF(k + 1, 0);
+      dg_tile_gemm(stage, lane, At(k + 1, k), ld, 0, -1, KEEP_ALL, At(k + 1, k), ld, 0, -1, KEEP_ALL, 1, -1.0, 1.0,
+                   At(k + 1, k + 1), ld, nullptr, 0);
+      __syncwarp();
+      stampF(k + 1, 1);
+      dg_factor_tile(stage, lane, At(k + 1, k + 1), ld, St(k + 1, k + 1), N, dv + (k + 1) * TS, a.info,
+                     a.blk0 * 128 + (k + 1) * TS);
+      stampF(k + 1, 2);
+    } else {
+      const int me = (gw - f - 1 + GW) % GW;  // 0 .. GW-2
+      const int m = nt - 1 - k;               // trailing tile rows / columns
+      const int ntask = m * (m + 1) / 2 - 1;  // without (k+1, k+1)
+      for (int u = me; u < ntask; u += GW - 1) {
+        // task u+1 of the column-major enumeration (jj, ii), 0 <= jj <= ii < m: column jj holds m - jj tiles
+        int rest = u + 1, jj = 0;
+        while (rest >= m - jj) {
+          rest -= m - jj;
+          ++jj;
+        }
+        const int i = k + 1 + jj + rest, j = k + 1 + jj;
+        dg_tile_gemm(stage, lane, At(i, k), ld, 0, -1, KEEP_ALL, At(j, k), ld, 0, -1, KEEP_ALL, 1, -1.0, 1.0, At(i, j), ld,
+                     nullptr, 0);
+      }
+      stampT(k, 4);
+    }
+  }
+  int lvl = 0;
+
+  // ------------------------------------------------------------------ inverse: bottom-up merges on the 32-tile grid
+#pragma unroll 1
+  for (int h = 1; h < nt; h *= 2) {
+    const long ldw = (long)h * TS;
+    const int nodes = (nt + 2 * h - 1) / (2 * h);
+    // stage 1: W^T(i, j) = sum_{t >= i} U11(i, t) L21(j, t)^T
+    {
+      int base = 0;
+      for (int q = 0; q < nodes; ++q) {
+        const int a0 = 2 * h * q, c0 = a0 + h;
+        if (c0 >= nt) break;
+        const int s2 = min(h, nt - c0);
+        double* Wq = a.W + (size_t)q * ldw * ldw;
+        const int cnt = h * s2;
+        for (int u = ((gw - base) % GW + GW) % GW; u < cnt; u += GW) {  // task base + u goes to warp (base + u) mod GW
+          const int i = u % h, j = u / h;
+          dg_tile_gemm(stage, lane, St(a0 + i, a0 + i), N, (long)TS * N, 0, KEEP_UPPER, At(c0 + j, a0 + i), ld,
+                       (long)TS * ld, -1, KEEP_ALL, h - i, 1.0, 0.0, Wq + (size_t)i * TS + (size_t)j * TS * ldw, ldw,
+                       nullptr, 0);
+        }
+        base += cnt;
+      }
+    }
+    stampT(nt, 4 * lvl + 0);
+    cluster_barrier();
+    stampT(nt, 4 * lvl + 1);
+    // stage 2: X21(i, j) = - sum_{t <= i} X22(i, t) W^T(j, t)^T, U12 = X21^T
+    {
+      int base = 0;
+      for (int q = 0; q < nodes; ++q) {
+        const int a0 = 2 * h * q, c0 = a0 + h;
+        if (c0 >= nt) break;
+        const int s2 = min(h, nt - c0);
+        const double* Wq = a.W + (size_t)q * ldw * ldw;
+        const int cnt = h * s2;
+        for (int u = ((gw - base) % GW + GW) % GW; u < cnt; u += GW) {
+          const int i = u % s2, j = u / s2;
+          dg_tile_gemm(stage, lane, St(c0 + i, c0), N, (long)TS * N, i, KEEP_LOWER, Wq + (size_t)j * TS, ldw,
+                       (long)TS * ldw, -1, KEEP_ALL, i + 1, -1.0, 0.0, St(c0 + i, a0 + j), N, St(a0 + j, c0 + i), N);
+        }
+        base += cnt;
+      }
+    }
+    stampT(nt, 4 * lvl + 2);
+    cluster_barrier();
+    stampT(nt, 4 * lvl + 3);
+    ++lvl;
+  }
+
+  // ------------------------------------------------------------------ output layout of the dense engine
+  for (int j = crank * WARPS + warp; j < (int)N; j += GW) {
+    const int bj = j >> 7;
+    const double* src = a.S + (size_t)j * N;
+#pragma unroll 1
+    for (int i0 = 0; i0 < (int)N; i0 += 256) {
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (i0 + 32 * q < (int)N) ? __ldcg(src + i0 + 32 * q + lane) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = i0 + 32 * q + lane;
+        if (i0 + 32 * q >= (int)N) break;
+        if ((i >> 7) == bj) {
+          const size_t o = (size_t)(a.blk0 + bj) * 128 * 128 + (size_t)(j & 127) * 128 + (i & 127);
+          a.DX[o] = (i >= j) ? v[q] : 0.0;
+          a.DU[o] = (i <= j) ? v[q] : 0.0;
+        } else {
+          Ab[i + (size_t)j * ld] = v[q];
+        }
+      }
+    }
+  }
+  stampT(nt, 4 * lvl);
+}
+
+inline int configure_diag_kernel() {
+  ACE_CUDA(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg::SMEM_BYTES));
+  return 0;
+}
+
+inline int launch_diag_block(const DiagArgs& a, cudaStream_t st) {
+  diag_block_kernel<<<dg::NC, dg::THREADS, dg::SMEM_BYTES, st>>>(a);
+  ACE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ace

@@ -40,6 +40,19 @@ static int ncs_design(const double* x, int n, const double* knots_in, int nknots
   return K;
 }
 
+// Armadillo's arrayops::accumulate: two running sums over the even / odd elements (what arma::mean, arma::sum
+// and arma::accu of a contiguous vector reduce to)
+static double arma_accumulate(const double* x, int n) {
+  double acc1 = 0.0, acc2 = 0.0;
+  int i, j;
+  for (i = 0, j = 1; j < n; i += 2, j += 2) {
+    acc1 += x[i];
+    acc2 += x[j];
+  }
+  if (i < n) acc1 += x[i];
+  return acc1 + acc2;
+}
+
 static double col_median(const double* c, int n) {
   std::vector<double> t(c, c + n);
   std::sort(t.begin(), t.end());
@@ -88,9 +101,7 @@ int ace_normalize_train(double* y, double* X, double* Z, int n, int px, int pz, 
       }
     }
   }
-  double s = 0.0;
-  for (int r = 0; r < n; ++r) s += y[r];
-  M(0, 0) = s / n;
+  M(0, 0) = arma_accumulate(y, n) / n;                          // :69 mean(y)
   for (int r = 0; r < n; ++r) y[r] -= M(0, 0);
   for (int i = 1; i <= px + pz; ++i) {                         // :71-82
     if (isbinary[i - 1] == 0) {
@@ -99,15 +110,19 @@ int ace_normalize_train(double* y, double* X, double* Z, int n, int px, int pz, 
       for (int r = 0; r < n; ++r) c[r] -= M(i, 0);
     }
   }
-  {                                                            // :84-85  arma::stddev, n-1 form
-    double mean = 0.0;
-    for (int r = 0; r < n; ++r) mean += y[r];
-    mean /= n;
+  {                                                            // :84-85  arma::stddev, n-1 form (op_var::direct_var)
+    const double mean = arma_accumulate(y, n) / n;
     double a2 = 0.0, a3 = 0.0;
-    for (int r = 0; r < n; ++r) {
-      const double t = mean - y[r];
-      a2 += t * t;
-      a3 += t;
+    int i, j;
+    for (i = 0, j = 1; j < n; i += 2, j += 2) {
+      const double ti = mean - y[i], tj = mean - y[j];
+      a2 += ti * ti + tj * tj;
+      a3 += ti + tj;
+    }
+    if (i < n) {
+      const double ti = mean - y[i];
+      a2 += ti * ti;
+      a3 += ti;
     }
     M(0, 1) = std::sqrt((a2 - a3 * a3 / n) / (n - 1));
     for (int r = 0; r < n; ++r) y[r] /= M(0, 1);

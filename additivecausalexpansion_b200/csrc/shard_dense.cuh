@@ -171,8 +171,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     }
     tr.mark(J, 0, w.side);
     if (mine) {
-      ACE_TRY(potrf_rec(w, j0, j1, w.side));
-      ACE_TRY(trtri_merge_range(w, j0, j1, w.side, w.Wsmall));  // X_JJ / U_JJ in place (early low merge levels)
+      ACE_TRY(diag_block_factor_invert(w, j0, j1, w.side));  // L_JJ, X_JJ / U_JJ in place
       ACE_CUDA(cudaMemcpy2DAsync(Hd, sizeof(double) * hJ, blkptr(w, j0, j0), sizeof(double) * w.ld,
                                  sizeof(double) * wJ, (size_t)wJ, cudaMemcpyDeviceToDevice, w.side));
       if (wN > 0) {
@@ -258,19 +257,27 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     // as two batched GEMMs over the owned panels (Wt_c = U[c rows, c0:j0] * L[J, c0:j0]^T; X[J,c] = -X_JJ Wt_c^T,
     // with the transposed copy U[c rows, J]).  A rank only ever needs its own columns of X: no exchange until the end.
     if (cx.incr && J >= 1 && w.bg) {
-      // emulation plays every rank in turn with the SAME world-strided batches a real rank launches
+      // Emulation plays every rank in turn with the SAME world-strided batches a real rank launches.  All first
+      // products run before any second one: a real rank overwrites L[J, its panels] with X in its own copy of A,
+      // here the one shared A must keep block row J of L until every played rank has read it.
       const int Gs = cx.world;
+      const int r_lo = cx.emulate ? 0 : cx.rank, r_hi = cx.emulate ? cx.world : cx.rank + 1;
+      const long pw = (long)pb * TB, step = (long)Gs * pw;
+      // few tiles (32 per problem) with a K range that grows to n: split K into chunks of <= 2048 so that the
+      // background work is spread over the SMs instead of running as a handful of millisecond-long tiles
+      const int KL = 2048;
+      const int S = std::max(1, (j0 * TB + KL - 1) / KL);
+      const size_t len = (size_t)pw * wJ;
+      auto count_of = [&](int cf) { return (cf < J) ? (J - cf + Gs - 1) / Gs : 0; };
+      size_t total_cnt = 0;
+      for (int cf = r_lo; cf < r_hi; ++cf) total_cnt += (size_t)count_of(cf);
       ACE_CUDA(cudaStreamWaitEvent(w.bg, ev_copy[J], 0));  // block row J of L and X_JJ are in A (copies are in order)
-      for (int cf = cx.emulate ? 0 : cx.rank; cf < (cx.emulate ? cx.world : cx.rank + 1); ++cf) {
-        const int cnt = (cf < J) ? (J - cf + Gs - 1) / Gs : 0;
+      size_t off = 0;
+      for (int cf = r_lo; cf < r_hi; ++cf) {
+        const int cnt = count_of(cf);
         if (cnt <= 0) continue;
-        const long pw = (long)pb * TB, step = (long)Gs * pw;
-        // few tiles (32 per problem) with a K range that grows to n: split K into chunks of <= 2048 so that the
-        // background work is spread over the SMs instead of running as a handful of millisecond-long tiles
-        const int KL = 2048;
-        const int S = std::max(1, (j0 * TB + KL - 1) / KL);
-        const size_t len = (size_t)pw * wJ;
-        double* part = (S > 1) ? w.Bf + (size_t)cnt * len : w.Bf;  // partials behind the summed Wt
+        double* Wt = w.Bf + off * len;
+        double* part = (S > 1) ? w.Bf + total_cnt * len : Wt;  // partials behind all the summed Wt
         GemmNT p{};
         p.A = w.A + (size_t)cf * pw; p.lda = w.ld; p.a_tri = 1; p.a_row_off = (int)(cf * pw); p.s_row_off = (int)step;
         p.Adiag = w.DU;
@@ -284,17 +291,24 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
         ACE_TRY(launch_gemm_nt(p, w.bg));
         if (S > 1) {
           const size_t total = (size_t)cnt * len;
-          splitk_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, w.bg>>>(part, S, len, total, w.Bf);
+          splitk_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, w.bg>>>(part, S, len, total, Wt);
           ACE_CUDA(cudaGetLastError());
         }
+        off += (size_t)cnt;
+      }
+      off = 0;
+      for (int cf = r_lo; cf < r_hi; ++cf) {
+        const int cnt = count_of(cf);
+        if (cnt <= 0) continue;
         GemmNT r{};
         r.A = blkptr(w, j0, j0); r.lda = w.ld; r.a_tri = 2; r.Adiag = w.DX + (size_t)j0 * TB * TB;
-        r.B = w.Bf; r.ldb = pw;
+        r.B = w.Bf + off * len; r.ldb = pw;
         r.C = blkptr(w, j0, cf * pb); r.ldc = w.ld;
         r.Ct = blkptr(w, cf * pb, j0); r.ldct = w.ld;
         r.M = (int)wJ; r.N = (int)pw; r.K = (int)wJ; r.alpha = -1.0; r.beta = 0.0;
         r.batch = cnt; r.sA = 0; r.sB = pw * wJ; r.sC = step * w.ld; r.sCt = step;
         ACE_TRY(launch_gemm_nt(r, w.bg));
+        off += (size_t)cnt;
       }
       ACE_CUDA(cudaEventRecord(w.ev_aux, w.bg));
     }

@@ -150,19 +150,26 @@ int ace_fit_run(ace_fit* fit, int iter_start, int max_iter, double tol, double p
  * parameters; the stored inverse (invKmatn) is left untouched, as in the reference. */
 int ace_fit_get_train_stats(ace_fit* fit, double* stats);
 
-/* Multi-GPU sharding of ONE fit over `world` GPUs of a node (one process per GPU):
- * the kernel build is split into 2*world column blocks (rank r builds blocks r and 2*world-1-r, lower
- * trapezoids only) that are exchanged with NCCL broadcasts over NVLink; the Cholesky / inverse run
- * redundantly on every rank; the gradient pass takes every world-th tile and its P sums + K*alpha are
- * all-reduced, so all ranks hold bit-identical parameters after every iteration.
+/* Multi-GPU sharding of ONE fit over `world` GPUs of a node (one process per GPU).
+ * Every phase of the iteration is split and every rank ends an iteration with bit-identical parameters:
+ *   - Cholesky: right-looking over 512-wide column panels dealt cyclically (panel J to rank J mod world); the owner
+ *     factors and inverts the diagonal block, solves the rows below and broadcasts the panel over NVLink in two
+ *     pieces (head: what the next owner needs at once; bulk: the rest, on a second communicator);
+ *   - kernel build: a rank builds exactly the K columns of the panels it owns -- K itself is never exchanged;
+ *   - triangular inverse: grown behind the panels per column owner + ONE all-gather (or, when the trailing updates
+ *     dominate, a merge tree whose upper levels are split over the ranks with one all-gather per level);
+ *   - K^-1 = U U^T and the gradient pass: tiles dealt round-robin, nothing exchanged but the P sums + K*alpha of
+ *     the gradient (one all-reduce per iteration).
  * ace_comm_unique_id: rank 0 creates the 128-byte NCCL id and distributes it out of band;
- * ace_shard_plan: the two column blocks (of `width` columns of the 128-padded matrix) a rank builds (host only);
- * ace_fit_shard: every rank joins the communicator; needs ceil(n/128)*128 divisible by 128*world. */
+ * ace_shard_plan: the two column blocks (of `width` columns of the 128-padded matrix) rank `rank` takes in the
+ *   block-paired split (blocks r and 2*world-1-r: equal work on lower trapezoids) -- host only;
+ * ace_fit_shard: every rank joins the communicators; needs ceil(n/128)*128 divisible by 128*world. */
 int ace_comm_unique_id(char* id128);
 int ace_shard_plan(int n, int world, int rank, int* blocks2, int* width);
 int ace_fit_shard(ace_fit* fit, const char* id128, int rank, int world);
-/* Single-process stand-in for a `world`-rank sharded fit: this process plays every rank in turn on its one GPU (no
- * NCCL); numerically identical to the multi-GPU path, used by the single-GPU parity tests. */
+/* Single-process stand-in for a `world`-rank sharded fit: this process plays every rank in turn on its one GPU with
+ * the launches, tile subsets and packed buffers of a real rank but without NCCL (the exchanges are the shared memory
+ * of the one device); used by the single-GPU parity tests. */
 int ace_fit_shard_emulate(ace_fit* fit, int world);
 /* ACE_SHARD_TRACE=1: print the per-panel event timeline of the last sharded Cholesky to stderr (debug). */
 int ace_dbg_shard_trace_dump(int rank);
@@ -212,6 +219,9 @@ int ace_dbg_spd_inverse(const double* A, int n, double* L, double* inv, double* 
 int ace_bench_dense(int n, int reps, double* ms3);
 /* test hooks: stop the triangular-inverse merge after level h; raw state after potrf + trtri
  * (rawA n_pad x n_pad: X = L^-1 lower / U = L^-T upper; DX, DU: 128 x n_pad diagonal tiles; rawBf workspace) */
+int ace_dbg_spd_inverse_fused(const double* A, int n, double* inv, double* diagL);
+int ace_dbg_diag_block(const double* A, int n, double* X, double* U, double* diagL, double* Ldiag_tiles);
+int ace_dbg_diag_block_timeline(long long* stamps, int count);
 int ace_dbg_set_trtri_max_h(int h);
 int ace_dbg_trtri_raw(const double* A, int n, double* rawA, double* DX, double* DU, double* rawBf);
 

@@ -7,7 +7,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 ``ace_oracle.cpp`` is a literal C++ restatement of the reference's native files
 (file:line cited per function there); this module is the ctypes face of it with the
 reference's own function names and argument order (``R/RcppExports.R:4-78``).
-PARITY UNPINNED: the reference has no tests or golden vectors.
+The reference has no tests or golden vectors of its own.  What pins this restatement:
+``oracle/_ref/libace_ref.so`` -- the reference's OWN native sources (``/root/reference/src/*.cpp``) compiled
+unmodified against a small stand-in for the RcppArmadillo headers (``oracle/miniarma/``; R, Rcpp and Armadillo do
+not exist in the build container), driven through the same ctypes code (``using_reference()``);
+``tests/test_oracle_vs_reference.py`` compares the two function by function and ``tests/golden/ref_golden.npz``
+carries reference-generated vectors to machines that do not have ``/root/reference``.
 """
 from __future__ import annotations
 
@@ -67,6 +72,68 @@ def lib(nthreads: int = 0):
 
 def threads() -> int:
     return int(lib().ace_oracle_threads())
+
+
+# --------------------------------------------------------------------------- the compiled reference (oracle/_ref)
+REFERENCE_SRC = "/root/reference/src"
+_REF_LIB = None
+
+
+def reference_so() -> str:
+    return os.path.join(_HERE, "_ref", "libace_ref.so")
+
+
+def build_ref(force: bool = False):
+    """Compile the reference's own sources (where they lie under /root/reference/src) + oracle/ref_harness.cpp
+    against oracle/miniarma into oracle/_ref/libace_ref.so.  Returns the path, or None when the reference sources
+    are not on this machine and no prebuilt library travelled here."""
+    so = reference_so()
+    if os.path.isdir(REFERENCE_SRC):
+        deps = [os.path.join(_HERE, "ref_harness.cpp"), os.path.join(_HERE, "miniarma", "RcppArmadillo.h")]
+        stale = (not os.path.exists(so)) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps)
+        if force or stale:
+            subprocess.check_call(["make", "-C", _HERE, "_ref"] + (["-B"] if force else []),
+                                  stdout=subprocess.DEVNULL)
+    return so if os.path.exists(so) else None
+
+
+def reference_available() -> bool:
+    return build_ref() is not None
+
+
+def ref_lib(nthreads: int = 0):
+    global _REF_LIB
+    if _REF_LIB is None:
+        so = build_ref()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libace_ref.so is not available (the reference sources are not here)")
+        L = C.CDLL(so)
+        L.ace_oracle_init.argtypes = [C.c_char_p, C.c_int]
+        L.ace_oracle_init.restype = C.c_int
+        rc = L.ace_oracle_init(_find_openblas().encode(), int(nthreads))
+        if rc != 0:
+            raise RuntimeError(f"ace_ref init failed ({rc})")
+        L.ace_oracle_mu_solution.restype = C.c_double
+        L.ace_oracle_threads.restype = C.c_int
+        _REF_LIB = L
+    return _REF_LIB
+
+
+class using_reference:
+    """``with oracle.using_reference(): oracle.grad_SE_cpp(...)`` runs the per-function wrappers of this module on
+    the compiled reference sources instead of the restatement (the R-level sequencing -- OracleFit -- exists only in
+    the restatement: the reference keeps it in R)."""
+
+    def __enter__(self):
+        global _LIB
+        lib()
+        self._saved = _LIB
+        _LIB = ref_lib()
+        return self
+
+    def __exit__(self, *exc):
+        global _LIB
+        _LIB = self._saved
 
 
 def _f(a, ndim=None):
@@ -230,6 +297,23 @@ def ncs_basis_deriv(x, knots):
     out = np.empty((x.size, K), order="F")
     lib().ace_oracle_ncs_basis_deriv(_p(x), x.size, _p(knots), knots.size, _p(out))
     return out
+
+
+def normalize_train(y, X, Z):
+    """In place on y, X, Z (like the reference, src/utilities_cpp.cpp:13-104); returns the moments matrix."""
+    n, px = X.shape
+    pz = Z.shape[1]
+    assert y.flags.f_contiguous and X.flags.f_contiguous and Z.flags.f_contiguous
+    mo = np.zeros((1 + px + pz, 3), order="F")
+    lib().ace_oracle_normalize_train(_p(y), _p(X), _p(Z), n, px, pz, _p(mo))
+    return mo
+
+
+def normalize_test(X, Z, moments):
+    n, px = X.shape
+    pz = Z.shape[1]
+    assert X.flags.f_contiguous and Z.flags.f_contiguous
+    lib().ace_oracle_normalize_test(_p(X), _p(Z), n, px, pz, _p(_f(moments)))
 
 
 # --------------------------------------------------------------------------- R-level sequencing

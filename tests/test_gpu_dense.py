@@ -54,6 +54,48 @@ def test_spd_inverse(n):
     assert np.abs(inv @ A - np.eye(n)).max() <= 1e-9
 
 
+@pytest.mark.parametrize("n", [1, 31, 32, 100, 128, 200, 256, 300, 384, 500, 512])
+def test_diag_block_kernel(n):
+    """The cluster kernel that factors and inverts one diagonal block (csrc/diag_block.cuh) against NumPy."""
+    A = _spd(n, 100 + n, cond=1e4)
+    A = 0.5 * (A + A.T)
+    r = api.dbg_diag_block(A)
+    Lref = np.linalg.cholesky(A)
+    Xref = np.linalg.inv(Lref)
+    sx = np.abs(Xref).max()
+    assert np.abs(r["diagL"] - np.diag(Lref)).max() <= 1e-11 * np.abs(Lref).max()
+    assert np.abs(r["X"] - Xref).max() <= 1e-9 * sx, np.abs(r["X"] - Xref).max() / sx
+    assert np.array_equal(r["U"], r["X"].T)
+    mask = np.zeros((n, n), dtype=bool)
+    for b in range(0, n, 128):
+        mask[b:b + 128, b:b + 128] = True
+    assert np.abs(r["Ldiag"] - np.tril(Lref) * mask).max() <= 1e-11 * np.abs(Lref).max()
+    assert np.abs(r["X"] @ Lref - np.eye(n)).max() <= 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 7, 129, 300, 512, 513, 640, 1000, 1536, 2048, 2500])
+def test_spd_inverse_production_schedule(n):
+    A = _spd(n, n + 7)
+    A = 0.5 * (A + A.T)
+    r = api.dbg_spd_inverse_fused(A)
+    Lref = np.linalg.cholesky(A)
+    iref = np.linalg.inv(A)
+    assert np.abs(r["diagL"] - np.diag(Lref)).max() <= 1e-11 * np.abs(Lref).max()
+    assert np.abs(r["inv"] - iref).max() <= 1e-10 * np.abs(iref).max()
+    assert np.array_equal(r["inv"], r["inv"].T)
+    assert np.abs(r["inv"] @ A - np.eye(n)).max() <= 1e-9
+
+
+def test_diag_block_kernel_reports_first_bad_pivot():
+    n = 300
+    A = _spd(n, 5)
+    A = 0.5 * (A + A.T)
+    A[170, 170] = -1.0
+    with pytest.raises(api.AceError) as e:
+        api.dbg_diag_block(A)
+    assert e.value.status == 171
+
+
 def test_invkernel_cpp_matches_logdet_and_inverse():
     n = 777
     K = _spd(n, 3, cond=1e5)
