@@ -97,6 +97,7 @@ SIGNATURES = {
     "ace_fit_last_timing": (_i, [_vp, _p]),
     "ace_fit_predict": (_i, [_vp, _p, _p, _i, _d, _d, _p, _p, _p]),
     "ace_fit_predict_marginal": (_i, [_vp, _p, _p, _p, _i, _d, _d, _d, _i, _p, _p, _p, _p]),
+    "ace_fit_predict_marginal_batch": (_i, [_vp, _p, _p, _p, _i, _d, _d, _d, C.POINTER(C.c_ubyte), _i, _p, _p, _p, _p, _ip]),
     "ace_dbg_gemm_nt": (_i, [_p, _p, _p, _i, _i, _i, _d, _d, _i]),
     "ace_dbg_spd_inverse": (_i, [_p, _i, _p, _p, _p, _p]),
     "ace_dbg_spd_inverse_fused": (_i, [_p, _i, _p, _p]),

@@ -225,12 +225,23 @@ namespace ace {
 
 // common tail of the marginal prediction: Kx (nx_pad x n_pad), Cm (nx_pad x nx_pad, the marginal K_xx) on device
 // Kinv == nullptr: factor form (posterior_rows_tri), T K_xX^T = W W^T
+// subsets / S / avgS / counts: optional batch of S row subsets (nx x S flags, HOST memory) whose averages are
+// evaluated on the sub-blocks of the one posterior covariance (ace_fit_predict_marginal_batch)
 static int marginal_tail(Core& c, const double* Kinv, const double* Kx, double* Cm, const double* zx_dev, int nx,
                          int nx_pad, double mu, double std_y, double std_Z, int calculate_ate, const double* Zx_host,
-                         double* map, double* ci, double* var, double* avg) {
-  DBuf<double> kd, q;
+                         double* map, double* ci, double* var, double* avg, const unsigned char* subsets = nullptr,
+                         int S = 0, double* avgS = nullptr, int* counts = nullptr) {
+  DBuf<double> kd, q, qS;
+  DBuf<unsigned char> dsub;
   ACE_TRY(kd.alloc(nx_pad));
   ACE_TRY(q.alloc(4));
+  std::vector<double> hqS((size_t)3 * std::max(S, 1), 0.0);
+  if (S > 0) {
+    calculate_ate = 1;
+    ACE_TRY(qS.alloc((size_t)3 * S));
+    ACE_TRY(dsub.alloc((size_t)nx * S));
+    ACE_CUDA(cudaMemcpyAsync(dsub.p, subsets, (size_t)nx * S, cudaMemcpyHostToDevice, c.st));
+  }
   diag_extract_kernel<<<(nx + 255) / 256, 256, 0, c.st>>>(Cm, nx_pad, nx, kd.p);
   ACE_CUDA(cudaGetLastError());
   PostOut o;
@@ -248,6 +259,11 @@ static int marginal_tail(Core& c, const double* Kinv, const double* Kx, double* 
     quadforms_kernel<<<1, 1024, 0, c.st>>>(Cm, nx_pad, nx, zx_dev, q.p);
     ACE_CUDA(cudaGetLastError());
     ACE_CUDA(cudaMemcpyAsync(hq, q.p, sizeof(double) * 3, cudaMemcpyDeviceToHost, c.st));
+    if (S > 0) {
+      quadforms_subset_kernel<<<S, 1024, 0, c.st>>>(Cm, nx_pad, nx, zx_dev, dsub.p, qS.p);
+      ACE_CUDA(cudaGetLastError());
+      ACE_CUDA(cudaMemcpyAsync(hqS.data(), qS.p, sizeof(double) * 3 * S, cudaMemcpyDeviceToHost, c.st));
+    }
   }
   std::vector<double> hm(nx), hv(nx);
   ACE_CUDA(cudaMemcpyAsync(hm.data(), o.map.p, sizeof(double) * nx, cudaMemcpyDeviceToHost, c.st));
@@ -260,29 +276,41 @@ static int marginal_tail(Core& c, const double* Kinv, const double* Kx, double* 
     ci[i + nx] = map[i] + 1.96 * sd;
     var[i] = sd * sd;
   }
-  if (calculate_ate && avg) {  // src/pred_cpp.cpp:86-110
+  // averages over a row set (all rows: flags == nullptr), src/pred_cpp.cpp:86-110
+  auto averages = [&](const unsigned char* flags, const double* quad, double* out, int* cnt) {
     double s = 0.0, sz = 0.0, dz = 0.0;
+    int ns = 0;
     for (int i = 0; i < nx; ++i) {
+      if (flags && !flags[i]) continue;
+      ++ns;
       s += map[i];
       sz += Zx_host[i];
       dz += map[i] * Zx_host[i];
     }
-    const double ate = s / (double)nx;
-    const double ate_sd = std_y * std::sqrt(hq[0]) / (double)nx;
+    const double ate = s / (double)ns;
+    const double ate_sd = std_y * std::sqrt(quad[0]) / (double)ns;
     const unsigned int ntx = (unsigned int)sz;
     const double att = dz / ntx;
-    const double att_sd = std_y * std::sqrt(hq[1]) / ntx;
-    const unsigned int nux = (unsigned int)nx - ntx;
-    const double atu = (ate * (double)nx - att * ntx) / nux;
-    const double atu_sd = std_y * std::sqrt(hq[2]) / nux;
+    const double att_sd = std_y * std::sqrt(quad[1]) / ntx;
+    const unsigned int nux = (unsigned int)ns - ntx;
+    const double atu = (ate * (double)ns - att * ntx) / nux;
+    const double atu_sd = std_y * std::sqrt(quad[2]) / nux;
     const double vals[3] = {ate, att, atu}, sds[3] = {ate_sd, att_sd, atu_sd};
     for (int k = 0; k < 3; ++k) {
-      avg[4 * k] = vals[k];
-      avg[4 * k + 1] = vals[k] - 1.96 * sds[k];
-      avg[4 * k + 2] = vals[k] + 1.96 * sds[k];
-      avg[4 * k + 3] = sds[k] * sds[k];
+      out[4 * k] = vals[k];
+      out[4 * k + 1] = vals[k] - 1.96 * sds[k];
+      out[4 * k + 2] = vals[k] + 1.96 * sds[k];
+      out[4 * k + 3] = sds[k] * sds[k];
     }
-  }
+    if (cnt) {
+      cnt[0] = ns;
+      cnt[1] = (int)ntx;
+      cnt[2] = (int)nux;
+    }
+  };
+  if (calculate_ate && avg) averages(nullptr, hq, avg, nullptr);
+  for (int sidx = 0; sidx < S; ++sidx)
+    averages(subsets + (size_t)sidx * nx, hqS.data() + 3 * sidx, avgS + 12 * sidx, counts ? counts + 3 * sidx : nullptr);
   return 0;
 }
 
@@ -333,10 +361,9 @@ int ace_pred_marginal_cpp(const double* y_X, const double* Z_x, double sigma, do
                        avg);
 }
 
-int ace_fit_predict_marginal(ace_fit* f, const double* X2, const double* Z2, const double* dZ2, int nx, double mean_y,
-                             double std_y, double std_Z, int calculate_ate, double* map, double* ci, double* var,
-                             double* avg) {
-  (void)mean_y;
+static int fit_predict_marginal(ace_fit* f, const double* X2, const double* Z2, const double* dZ2, int nx,
+                                double std_y, double std_Z, int calculate_ate, double* map, double* ci, double* var,
+                                double* avg, const unsigned char* subsets, int S, double* avgS, int* counts) {
   if (!f || !X2 || !Z2 || !dZ2 || !map || !ci || !var || nx < 1) return usage("predict_marginal: bad argument");
   Core& c = f->c;
   ACE_CUDA(cudaSetDevice(c.device));
@@ -370,7 +397,24 @@ int ace_fit_predict_marginal(ace_fit* f, const double* X2, const double* Z2, con
   ACE_TRY(sync_stream(c.st));
   if (!c.u_valid) ACE_TRY(c.ensure_full_inverse());
   return marginal_tail(c, c.u_valid ? nullptr : c.Bf.p, Kx.p, Cm.p, zx.p, nx, nx_pad, hpar[1], std_y, std_Z, calculate_ate, Z2, map, ci,
-                       var, avg);
+                       var, avg, subsets, S, avgS, counts);
+}
+
+int ace_fit_predict_marginal(ace_fit* f, const double* X2, const double* Z2, const double* dZ2, int nx, double mean_y,
+                             double std_y, double std_Z, int calculate_ate, double* map, double* ci, double* var,
+                             double* avg) {
+  (void)mean_y;
+  return fit_predict_marginal(f, X2, Z2, dZ2, nx, std_y, std_Z, calculate_ate, map, ci, var, avg, nullptr, 0, nullptr,
+                              nullptr);
+}
+
+int ace_fit_predict_marginal_batch(ace_fit* f, const double* X2, const double* Z2, const double* dZ2, int nx,
+                                   double mean_y, double std_y, double std_Z, const unsigned char* subsets, int S,
+                                   double* map, double* ci, double* var, double* avg, int* counts) {
+  (void)mean_y;
+  if (!subsets || S < 1 || !avg) return usage("predict_marginal_batch: bad argument");
+  double all[12];
+  return fit_predict_marginal(f, X2, Z2, dZ2, nx, std_y, std_Z, 1, map, ci, var, all, subsets, S, avg, counts);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -173,4 +173,36 @@ __global__ void __launch_bounds__(1024) quadforms_kernel(const double* __restric
   }
 }
 
+// one CTA per subset s (0/1 flags m = subsets + s * nx): q[3 s + 0] = m' C m, q[3 s + 1] = (m o z)' C (m o z),
+// q[3 s + 2] = (m o 1[z == 0])' C (m o 1[z == 0]): the quadratic forms of src/pred_cpp.cpp:89,98,107 on the
+// sub-block C[m, m] that a separate prediction on the subset would form
+__global__ void __launch_bounds__(1024) quadforms_subset_kernel(const double* __restrict__ C, long ld, int nx,
+                                                                const double* __restrict__ z,
+                                                                const unsigned char* __restrict__ subsets,
+                                                                double* __restrict__ q) {
+  __shared__ double red[32];
+  const unsigned char* m = subsets + (size_t)blockIdx.x * nx;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int j = 0; j < nx; ++j) {
+    if (!m[j]) continue;  // uniform over the CTA
+    const double zj = z[j];
+    const double* col = C + (size_t)j * ld;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+      if (!m[i]) continue;
+      const double c = col[i], zi = z[i];
+      s0 += c;
+      s1 = fma(zi * zj, c, s1);
+      s2 += (zi == 0.0 && zj == 0.0) ? c : 0.0;
+    }
+  }
+  s0 = block_sum_1024(s0, red);
+  s1 = block_sum_1024(s1, red);
+  s2 = block_sum_1024(s2, red);
+  if (threadIdx.x == 0) {
+    q[3 * blockIdx.x + 0] = s0;
+    q[3 * blockIdx.x + 1] = s1;
+    q[3 * blockIdx.x + 2] = s2;
+  }
+}
+
 }  // namespace ace

@@ -199,3 +199,26 @@ class AceFit:
             for k, name in enumerate(("ate", "att", "atu")):
                 out[name] = {"map": avg[4 * k], "ci": avg[4 * k + 1:4 * k + 3].copy(), "var": avg[4 * k + 3]}
         return out
+
+    def predict_marginal_batch(self, X2, Z2, dZ2, subsets, mean_y=0.0, std_y=1.0, std_Z=1.0):
+        """Marginal posterior of the nx points + ATE / ATT / ATU of S row subsets from ONE kernel build and ONE posterior
+        covariance (ace_fit_predict_marginal_batch): what robust_treatment's n.steps + 1 predict.ace calls compute
+        (R/robust_treatment.R:93-128).  subsets: nx x S boolean.  Returns the full-set dict plus "subsets": a list of
+        {"n", "n_treated", "n_untreated", "ate", "att", "atu"} in the reference's {"map", "ci", "var"} form."""
+        X2, Z2, dZ2 = _f(X2, True), _f(Z2, True), _f(dZ2, True)
+        nx = X2.shape[0]
+        sub = np.asfortranarray(np.asarray(subsets).reshape(nx, -1).astype(np.uint8))
+        S = sub.shape[1]
+        m, ci, var = np.empty(nx), np.empty((nx, 2), order="F"), np.empty(nx)
+        avg, cnt = np.zeros((S, 12)), np.zeros((S, 3), dtype=np.int32)
+        check(lib().ace_fit_predict_marginal_batch(
+            self._h, _p(X2), _p(Z2), _p(dZ2), nx, float(mean_y), float(std_y), float(std_Z),
+            sub.ctypes.data_as(C.POINTER(C.c_ubyte)), S, _p(m), _p(ci), _p(var), _p(avg),
+            cnt.ctypes.data_as(C.POINTER(C.c_int))), "ace_fit_predict_marginal_batch")
+        out = {"map": m, "ci": ci, "var": var, "subsets": []}
+        for s in range(S):
+            d = {"n": int(cnt[s, 0]), "n_treated": int(cnt[s, 1]), "n_untreated": int(cnt[s, 2])}
+            for k, name in enumerate(("ate", "att", "atu")):
+                d[name] = {"map": avg[s, 4 * k], "ci": avg[s, 4 * k + 1:4 * k + 3].copy(), "var": avg[s, 4 * k + 3]}
+            out["subsets"].append(d)
+        return out

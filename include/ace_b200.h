@@ -204,6 +204,17 @@ int ace_fit_predict(ace_fit* fit, const double* X2, const double* Z2, int nx, do
 int ace_fit_predict_marginal(ace_fit* fit, const double* X2, const double* Z2, const double* dZ2, int nx,
                              double mean_y, double std_y, double std_Z, int calculate_ate, double* map,
                              double* ci, double* var, double* avg);
+/* Batched marginal posterior for callers that predict on many SUBSETS of one point set: robust_treatment
+ * (R/robust_treatment.R:93-128) issues n.steps + 1 calls predict.ace(marginal = TRUE, return_average_treatments = TRUE)
+ * on variance-filtered subsets of the same points, each rebuilding K_xX and K_xx.  Here ONE kernel build, ONE triangular
+ * product with the resident factor and ONE posterior covariance serve all subsets: the per-point rows of a subset are
+ * rows of the full result and its ATE / ATT / ATU use the sub-block C[m, m] (src/pred_cpp.cpp:86-110).
+ * subsets: nx x S flags (0/1), column-major.  map / ci / var: the nx points (as ace_fit_predict_marginal on all of them).
+ * avg: S x 12 = {ate, att, atu} x {map, ci lo, ci hi, var} per subset;  counts (optional): S x 3 = points, treated,
+ * untreated of each subset.  Z2's first column is the 0/1 treatment Z_x of pred_marginal_cpp. */
+int ace_fit_predict_marginal_batch(ace_fit* fit, const double* X2, const double* Z2, const double* dZ2, int nx,
+                                   double mean_y, double std_y, double std_Z, const unsigned char* subsets, int S,
+                                   double* map, double* ci, double* var, double* avg, int* counts);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense building blocks, exported for tests and benchmarks (host in / host out)

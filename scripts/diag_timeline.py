@@ -37,3 +37,8 @@ for i, v in enumerate(flat):
         break
     print(f"  stamp {i}: +{(v - prev) / GHZ / 1e3:7.2f} us   at {(v - t0) / GHZ / 1e3:8.2f}")
     prev = v
+
+pc = np.array(buf[240:246], dtype=np.int64)
+pt = np.array(buf[280:287], dtype=np.int64)
+print("chol tile 0 probes (cycles): load->", np.diff(pc).tolist(), " = cols 0-3 | 4-7 | 8-15 | 16-31 | L out")
+print("trsm tile (1,0) probes (cycles):", np.diff(pt).tolist(), " = load factor | cols 0-7 | 8-15 | 16-23 | 24-31 | store")

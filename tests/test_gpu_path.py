@@ -223,3 +223,39 @@ def test_full_size_properties_c2():
         sign, logdet = np.linalg.slogdet(A)
         ev = -0.5 * (prob.n * np.log(2 * np.pi) + logdet + prob.y @ alpha)
         assert abs(st[1] - ev) <= RTOL * abs(ev)
+
+
+def test_predict_marginal_batch_matches_oracle_loop():
+    """robust_treatment's loop (R/robust_treatment.R:93-128): n.steps + 1 marginal predictions with ATE / ATT / ATU on
+    variance-filtered subsets of one point set.  One batched call (shared K_xX build, one posterior covariance) against
+    an oracle loop over pred_marginal_cpp on each subset."""
+    prob = synth.make_problem("C1", binary_z=True)
+    with AceFit(prob.y, prob.X, prob.Z, prob.parameters, kernel="SE", std_y=prob.std_y) as g:
+        for it in range(1, 4):
+            g.para_update(it)
+        par, invK = g.parameters, g.invKmatn
+        rng = np.random.default_rng(21)
+        nx, n_steps = 173, 5
+        X2 = np.asfortranarray(rng.uniform(-1, 1, (nx, prob.p)))
+        z2 = (rng.random(nx) < 0.45).astype(float)
+        tb = prob.basis.testbasis(z2)
+        full = g.predict_marginal(X2, tb["B"], tb["dB"], prob.mean_y, prob.std_y, 1.0, True)
+        # the reference's subsets: points whose marginal variance is below the quantile steps
+        steps = np.quantile(full["var"], np.linspace(0, 1, n_steps + 1))
+        subsets = np.stack([full["var"] <= s for s in steps], axis=1)
+        out = g.predict_marginal_batch(X2, tb["B"], tb["dB"], subsets, prob.mean_y, prob.std_y, 1.0)
+        assert np.array_equal(out["map"], full["map"]) and np.array_equal(out["var"], full["var"])
+        for s in range(n_steps + 1):
+            idx = subsets[:, s]
+            Xs, zs = np.asfortranarray(X2[idx]), z2[idx]
+            dBs = np.asfortranarray(tb["dB"][idx])
+            kxm = oracle.kernmat_SE_cpp(Xs, prob.X, dBs, prob.Z, par)
+            kxxm = oracle.kernmat_SE_symmetric_cpp(Xs, dBs, par)
+            mo = oracle.pred_marginal_cpp(prob.y, zs, par[0], par[1], invK, kxm["elements"], kxxm["elements"],
+                                          prob.mean_y, prob.std_y, 1.0, True)
+            got = out["subsets"][s]
+            assert got["n"] == int(idx.sum()) and got["n_treated"] == int(zs.sum())
+            assert np.abs(out["map"][idx] - mo["map"]).max() <= RTOL * np.abs(mo["map"]).max()
+            for k in ("ate", "att", "atu"):
+                assert _close(got[k]["map"], mo[k]["map"], RTOL, 1e-3), (s, k, got[k]["map"], mo[k]["map"])
+                assert _close(got[k]["var"], mo[k]["var"], 1e-7), (s, k, got[k]["var"], mo[k]["var"])
