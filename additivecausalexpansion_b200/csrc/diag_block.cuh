@@ -255,52 +255,11 @@ __device__ __forceinline__ void dg_inv_rows(double (&r)[8][4], double* Ls, doubl
   }
 }
 
-// columns c = 8 CB .. 8 CB + 7 of the solve X L^T = A on one tile held in registers (cyclic layout): x_c = a_c / L_cc,
-// then a_m -= x_c L(m, c) for the columns m > c
-template <int CB>
-__device__ __forceinline__ void dg_trsm_cols(double (&r)[8][4], const double* Ls, const double* idg, double* colbuf,
-                                             int tx, int ty) {
-#pragma unroll 1
-  for (int jx = 0; jx < 8; ++jx) {
-    const int c = 8 * CB + jx;
-    double* cb = colbuf + (c & 1) * 32;
-    if (tx == jx) {
-      const double d = idg[c];
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const double x = r[a][CB] * d;
-        r[a][CB] = x;
-        cb[4 * a + ty] = x;
-      }
-    }
-    __syncwarp();
-    double xm[8], lc[4];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) xm[a] = cb[4 * a + ty];
-#pragma unroll
-    for (int b = CB; b < 4; ++b) lc[b] = Ls[8 * b + tx + c * 33];
-    lc[CB] = (tx > jx) ? lc[CB] : 0.0;  // columns <= c of the straddling block (incl. the owners' own column)
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = CB; b < 4; ++b) r[a][b] = fma(-xm[a], lc[b], r[a][b]);
-  }
-}
-
-// L_kk (lower triangle of the 32 x 32 tile at Lkk) -> Ls[32][33], idg = 1 / diag
-__device__ __forceinline__ void dg_load_factor(double* Ls, double* idg, const double* Lkk, long ld, int lane) {
-#pragma unroll 8
-  for (int c = 0; c < 32; ++c) Ls[lane + c * 33] = __ldcg(Lkk + lane + (size_t)c * ld);
-  __syncwarp();
-  idg[lane] = fast_rcp(Ls[lane + lane * 33]);
-  __syncwarp();
-}
-
-// One warp: Cholesky of the 32 x 32 diagonal tile at At (lower triangle used): L -> lower of At, diag(L) -> dv.
-__device__ __noinline__ void dg_chol_tile(double* sm, int lane, double* At, long ld, double* dv, int* info, int gidx0,
-                                          long long* probe = nullptr) {
-  double* Ls = sm;                 // [32][33]: columns of L
-  double* colbuf = sm + 32 * 33;   // 2 x 32: pivot column, double buffered
+// Writes L (lower of At), diag(L) -> dv, X = L^-1 (lower) and U = X^T (upper) -> St (full 32 x 32 tile).
+__device__ __noinline__ void dg_factor_tile(double* sm, int lane, double* At, long ld, double* St, long lds,
+                                            double* dv, int* info, int gidx0) {
+  double* Ls = sm;                 // [32][33]: strictly lower = L, strictly upper = U (filled by the inverse)
+  double* colbuf = sm + 32 * 33;   // 2 x 32: pivot column / row, double buffered
   double* dgl = colbuf + 64;       // L_jj
   double* idg = dgl + 32;          // 1 / L_jj
   const int tx = lane & 7, ty = lane >> 3;
@@ -309,19 +268,14 @@ __device__ __noinline__ void dg_chol_tile(double* sm, int lane, double* At, long
   for (int b = 0; b < 4; ++b)
 #pragma unroll
     for (int a = 0; a < 8; ++a) r[a][b] = __ldcg(At + (4 * a + ty) + (size_t)(8 * b + tx) * ld);
-  DG_PROBE(0);
   dg_chol_cols<0, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  DG_PROBE(1);
   dg_chol_cols<0, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  DG_PROBE(2);
   dg_chol_cols<1, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
   dg_chol_cols<1, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  DG_PROBE(3);
   dg_chol_cols<2, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
   dg_chol_cols<2, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
   dg_chol_cols<3, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
   dg_chol_cols<3, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  DG_PROBE(4);
   __syncwarp();
   // L out: column c, lane = row (coalesced)
 #pragma unroll 4
@@ -330,30 +284,18 @@ __device__ __noinline__ void dg_chol_tile(double* sm, int lane, double* At, long
     if (lane == c) __stcg(At + lane + (size_t)c * ld, dgl[c]);
   }
   dv[lane] = dgl[lane];
-  __syncwarp();
-  DG_PROBE(5);
-}
-
-// One warp: X = L_kk^-1 (lower) and U = X^T (upper) -> St (full 32 x 32 tile), from the factor stored at Lkk.
-__device__ __noinline__ void dg_inv_tile(double* sm, int lane, const double* Lkk, long ld, double* St, long lds) {
-  double* Ls = sm;                 // strictly lower = L, strictly upper = U (filled here)
-  double* rowbuf = sm + 32 * 33;
-  double* idg = rowbuf + 96;
-  const int tx = lane & 7, ty = lane >> 3;
-  dg_load_factor(Ls, idg, Lkk, ld, lane);
-  double r[8][4];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) r[a][b] = (4 * a + ty == 8 * b + tx) ? 1.0 : 0.0;
-  dg_inv_rows<0>(r, Ls, rowbuf, idg, tx, ty);
-  dg_inv_rows<1>(r, Ls, rowbuf, idg, tx, ty);
-  dg_inv_rows<2>(r, Ls, rowbuf, idg, tx, ty);
-  dg_inv_rows<3>(r, Ls, rowbuf, idg, tx, ty);
-  dg_inv_rows<4>(r, Ls, rowbuf, idg, tx, ty);
-  dg_inv_rows<5>(r, Ls, rowbuf, idg, tx, ty);
-  dg_inv_rows<6>(r, Ls, rowbuf, idg, tx, ty);
-  dg_inv_rows<7>(r, Ls, rowbuf, idg, tx, ty);
+  dg_inv_rows<0>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<1>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<2>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<3>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<4>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<5>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<6>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<7>(r, Ls, colbuf, idg, tx, ty);
   __syncwarp();
   // X (lower) / U (upper) tile out: column c, lane = row.  X(i, c) = U(c, i) = Ls[c + i * 33] for i > c.
 #pragma unroll 4
@@ -362,38 +304,6 @@ __device__ __noinline__ void dg_inv_tile(double* sm, int lane, const double* Lkk
     __stcg(St + lane + (size_t)c * lds, v);
   }
   __syncwarp();
-}
-
-// One warp: the tile at Aik <- Aik L_kk^-T by substitution against the factor stored at Lkk (in place).
-#define DG_PROBE(i) do { if (probe != nullptr && lane == 0) probe[i] = clock64(); } while (0)
-__device__ __noinline__ void dg_trsm_tile(double* sm, int lane, double* Aik, const double* Lkk, long ld,
-                                          long long* probe = nullptr) {
-  double* Ls = sm;
-  double* colbuf = sm + 32 * 33;
-  double* idg = colbuf + 96;
-  const int tx = lane & 7, ty = lane >> 3;
-  double r[8][4];
-#pragma unroll
-  for (int b = 0; b < 4; ++b)
-#pragma unroll
-    for (int a = 0; a < 8; ++a) r[a][b] = __ldcg(Aik + (4 * a + ty) + (size_t)(8 * b + tx) * ld);
-  DG_PROBE(0);
-  dg_load_factor(Ls, idg, Lkk, ld, lane);
-  DG_PROBE(1);
-  dg_trsm_cols<0>(r, Ls, idg, colbuf, tx, ty);
-  DG_PROBE(2);
-  dg_trsm_cols<1>(r, Ls, idg, colbuf, tx, ty);
-  DG_PROBE(3);
-  dg_trsm_cols<2>(r, Ls, idg, colbuf, tx, ty);
-  DG_PROBE(4);
-  dg_trsm_cols<3>(r, Ls, idg, colbuf, tx, ty);
-  DG_PROBE(5);
-#pragma unroll
-  for (int b = 0; b < 4; ++b)
-#pragma unroll
-    for (int a = 0; a < 8; ++a) __stcg(Aik + (4 * a + ty) + (size_t)(8 * b + tx) * ld, r[a][b]);
-  __syncwarp();
-  DG_PROBE(6);
 }
 
 __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2) diag_block_kernel(const DiagArgs a) {
@@ -431,66 +341,66 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
   };
 
   // ------------------------------------------------------------------ factorisation + inverse, interleaved
-  // Serial chain per tile column k:  Cholesky of the diagonal tile (one warp) -> barrier -> column solve
-  // L_ik = A_ik L_kk^-T by substitution (every warp one tile) -> barrier -> update of the next diagonal tile (the warp
-  // that will factor it).  Everything else hides behind it:
+  // Serial chain per tile column k:  Cholesky + inverse of the diagonal tile (one warp) -> barrier -> column solve
+  // L_ik = A_ik X_kk^T (every warp one tile product) -> barrier -> update of the next diagonal tile (the warp that will
+  // factor it).  Everything else hides behind it:
   //   * trailing update A_ij -= L_ik L_jk^T, dealt over the warps of the other CTAs;
-  //   * X_kk = L_kk^-1 (the warp that factored tile k, one slot later);
-  //   * the inverse X = L^-1, right-looking and in place in S, one tile column behind the factorisation: the upper
-  //     tile (j, i), j < i, first accumulates AccT(j, i) = sum_{t = j}^{i-1} U(j, t) L(i, t)^T (one term per tile
-  //     column t) and is then replaced by U(j, i) = X(i, j)^T with X(i, j) = -X_ii AccT(j, i)^T.
-  // Every task is ONE 32^3 tile product or substitution: no separate inverse phase, no long K loops.
-  auto row_of_X = [&](int t, int u) {  // X(t, u) = -X_tt AccT(u, t)^T, U(u, t) = X(t, u)^T     (u < t)
-    dg_tile_gemm(stage, lane, St(t, t), N, 0, 0, KEEP_LOWER, St(u, t), N, 0, -1, KEEP_ALL, 1, -1.0, 0.0, St(t, u), N,
-                 St(u, t), N);
-  };
-  auto accumulate = [&](int t, int i, int j) {  // AccT(j, i) (+)= U(j, t) L(i, t)^T          (j <= t < i)
-    dg_tile_gemm(stage, lane, St(j, t), N, 0, (j == t) ? 0 : -1, KEEP_UPPER, At(i, t), ld, 0, -1, KEEP_ALL, 1, 1.0,
-                 (j == t) ? 0.0 : 1.0, St(j, i), N, nullptr, 0);
-  };
+  //   * the inverse X = L^-1, right-looking and in place in S: the upper tile (j, i), j < i, first accumulates
+  //     AccT(j, i) = sum_{t = j}^{i-1} U(j, t) L(i, t)^T (one term per tile column t, as soon as row t of X is final)
+  //     and is then replaced by U(j, i) = X(i, j)^T with X(i, j) = -X_ii AccT(j, i)^T.
+  // Every task is ONE 32^3 tile product: no separate inverse phase, no long K loops, no extra barriers.
+  // (Measured alternatives, profiles/r02/diag_block_timeline.md: a bottom-up merge tree after the factorisation
+  // costs +140 us; solving the column by substitution against L_kk with X_kk computed one slot later takes the tile
+  // inverse off the chain but the rolled substitution is slower than the tile product: 433 vs 379 us per block.)
   if (gw == fw(0)) {
     stampF(0, 1);
-    dg_chol_tile(stage, lane, At(0, 0), ld, dv, a.info, a.blk0 * 128, a.dbg ? a.dbg + 240 : nullptr);
+    dg_factor_tile(stage, lane, At(0, 0), ld, St(0, 0), N, dv, a.info, a.blk0 * 128);
     stampF(0, 2);
   }
 #pragma unroll 1
   for (int k = 0; k < nt; ++k) {
     stampT(k, 0);
-    cluster_barrier();  // L_kk visible; trailing update, accumulations and X_{k-1,k-1} of the previous slot complete
+    cluster_barrier();  // L_kk, X_kk visible; trailing update and accumulations of step k-1 complete
     stampT(k, 1);
-    // column k of L (nt-1-k tiles) and row k-1 of X (k-1 tiles)
+    // column k of L: L_ik = A_ik X_kk^T (in place), and row k of X: X(k, j) = -X_kk AccT(j, k)^T, U(j, k) = X(k, j)^T
     {
-      const int nsolve = nt - 1 - k, nrow = (k >= 1) ? k - 1 : 0;
-      for (int u = gw; u < nsolve + nrow; u += GW) {
-        if (u < nsolve)
-          dg_trsm_tile(stage, lane, At(k + 1 + u, k), At(k, k), ld, (a.dbg && k == 0 && gw == 0) ? a.dbg + 280 : nullptr);
-        else row_of_X(k - 1, u - nsolve);
+      const int nsolve = nt - 1 - k;
+      for (int u = gw; u < nsolve + k; u += GW) {
+        if (u < nsolve) {
+          const int i = k + 1 + u;
+          dg_tile_gemm(stage, lane, At(i, k), ld, 0, -1, KEEP_ALL, St(k, k), N, 0, 0, KEEP_LOWER, 1, 1.0, 0.0, At(i, k), ld,
+                       nullptr, 0);
+        } else {
+          const int j = u - nsolve;
+          dg_tile_gemm(stage, lane, St(k, k), N, 0, 0, KEEP_LOWER, St(j, k), N, 0, -1, KEEP_ALL, 1, -1.0, 0.0, St(k, j), N,
+                       St(j, k), N);
+        }
       }
     }
     stampT(k, 2);
-    cluster_barrier();  // column k of L, row k-1 of X / column k-1 of U visible
+    cluster_barrier();  // column k of L and row k of X / column k of U visible
     stampT(k, 3);
     if (k + 1 >= nt) break;
-    const int f = fw(k + 1);  // the factoring warp is warp 0 of CTA f
+    // The warp that factors tile k+1 updates it and goes on factoring (look-ahead).  The warps of the OTHER CTAs share
+    //   trailing update  A_ij -= L_ik L_jk^T           for k < j <= i        (column-major order, without (k+1, k+1))
+    //   accumulation     AccT(j, i) (+)= U(j, k) L_ik^T  for j <= k < i
+    // (the factoring warp's CTA stays out of it: its SM's FP64 pipe belongs to the serial chain).
+    const int f = fw(k + 1);  // also the CTA rank of the factoring warp
     if (gw == f) {
       stampF(k + 1, 0);
       dg_tile_gemm(stage, lane, At(k + 1, k), ld, 0, -1, KEEP_ALL, At(k + 1, k), ld, 0, -1, KEEP_ALL, 1, -1.0, 1.0,
                    At(k + 1, k + 1), ld, nullptr, 0);
       __syncwarp();
       stampF(k + 1, 1);
-      dg_chol_tile(stage, lane, At(k + 1, k + 1), ld, dv + (k + 1) * TS, a.info, a.blk0 * 128 + (k + 1) * TS);
+      dg_factor_tile(stage, lane, At(k + 1, k + 1), ld, St(k + 1, k + 1), N, dv + (k + 1) * TS, a.info,
+                     a.blk0 * 128 + (k + 1) * TS);
       stampF(k + 1, 2);
-    } else if (gw == fw(k)) {
-      dg_inv_tile(stage, lane, At(k, k), ld, St(k, k), N);  // X_kk / U_kk: needed from the next slot on
     } else if (crank != f) {
-      // worker warps: the CTAs other than the factoring one (its SM's FP64 pipe belongs to the serial chain), without
-      // the warp that inverts tile k (always index NC-2 of the CTA-fastest enumeration)
-      constexpr int NWK = (NC - 1) * WARPS - 1;
-      const int raw = warp * (NC - 1) + (crank - f - 1 + NC) % NC;
-      const int me = raw - (raw > NC - 2 ? 1 : 0);
-      const int m = nt - 1 - k;                // trailing tile rows / columns
-      const int nupd = m * (m + 1) / 2 - 1;    // trailing update without (k+1, k+1)
-      const int nacc = (k >= 1) ? (m + 1) * k : 0;  // terms t = k-1: i = k .. nt-1, j = 0 .. k-1
+      constexpr int NWK = (NC - 1) * WARPS;                        // worker warps
+      const int me = warp * (NC - 1) + (crank - f - 1 + NC) % NC;  // 0 .. NWK-1, CTA index fastest
+      const int m = nt - 1 - k;                                    // trailing tile rows / columns
+      const int nupd = m * (m + 1) / 2 - 1;                        // without (k+1, k+1)
+      const int nacc = m * (k + 1);
       for (int u = me; u < nupd + nacc; u += NWK) {
         if (u < nupd) {
           // task u+1 of the column-major enumeration (jj, ii), 0 <= jj <= ii < m: column jj holds m - jj tiles
@@ -503,23 +413,14 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
           dg_tile_gemm(stage, lane, At(i, k), ld, 0, -1, KEEP_ALL, At(j, k), ld, 0, -1, KEEP_ALL, 1, -1.0, 1.0, At(i, j), ld,
                        nullptr, 0);
         } else {
-          const int v = u - nupd;
-          accumulate(k - 1, k + v % (m + 1), v / (m + 1));
+          const int v = u - nupd, i = k + 1 + v % m, j = v / m;
+          dg_tile_gemm(stage, lane, St(j, k), N, 0, (j == k) ? 0 : -1, KEEP_UPPER, At(i, k), ld, 0, -1, KEEP_ALL, 1, 1.0,
+                       (j == k) ? 0.0 : 1.0, St(j, i), N, nullptr, 0);
         }
       }
       stampT(k, 4);
     }
   }
-  // tail: X of the last diagonal tile and the last accumulation terms (t = nt-2), then the last row of X
-  if (gw == fw(nt - 1)) {
-    dg_inv_tile(stage, lane, At(nt - 1, nt - 1), ld, St(nt - 1, nt - 1), N);
-  } else if (nt >= 2) {
-    const int raw = (gw > fw(nt - 1)) ? gw - 1 : gw;  // the other GW-1 warps
-    for (int j = raw; j < nt - 1; j += GW - 1) accumulate(nt - 2, nt - 1, j);
-  }
-  cluster_barrier();
-  for (int u = gw; u < nt - 1; u += GW) row_of_X(nt - 1, u);
-  cluster_barrier();
   const int lvl = 0;
 
   // ------------------------------------------------------------------ output layout of the dense engine

@@ -18,7 +18,9 @@
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#include <cstdio>
 #include <iostream>
+#include <limits>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -125,6 +127,8 @@ struct Mat {
   double& operator()(uword r, uword c) { return mem[r + n_rows * c]; }
   const double& operator()(uword r, uword c) const { return mem[r + n_rows * c]; }
 
+  double* memptr() { return mem; }
+  const double* memptr() const { return mem; }
   uword size() const { return n_elem; }
   Mat& zeros() { std::fill(mem, mem + n_elem, 0.0); return *this; }
   Mat& ones() { std::fill(mem, mem + n_elem, 1.0); return *this; }
@@ -256,6 +260,8 @@ struct Cube {
     for (uword b = 0; b < s; ++b) sl.emplace_back(new Mat(mem + r * c * b, r, c));
   }
   Cube& zeros() { std::fill(mem, mem + n_elem, 0.0); return *this; }
+  double* memptr() { return mem; }
+  const double* memptr() const { return mem; }
   Mat& slice(uword b) { return *sl[b]; }
   const Mat& slice(uword b) const { return *sl[b]; }
   double& operator()(uword r, uword c, uword s) { return mem[r + n_rows * c + n_rows * n_cols * s]; }
@@ -265,6 +271,7 @@ typedef Cube cube;
 
 namespace datum {
 const double pi = 3.14159265358979323846264338327950288;
+const double nan = std::numeric_limits<double>::quiet_NaN();
 }
 
 // ---------------------------------------------------------------------------------------------- element-wise algebra
@@ -537,5 +544,37 @@ List List::create(const Args&... args) {
 
 inline void checkUserInterrupt() {}
 static std::ostream& Rcout = std::cout;
+
+// Rcpp::stop(fmt, ...): an R error; here a C++ exception carrying the formatted message
+struct exception : std::runtime_error {
+  explicit exception(const std::string& m) : std::runtime_error(m) {}
+};
+template <typename... Args>
+[[noreturn]] inline void stop(const char* fmt, Args... args) {
+  char buf[1024];
+  if (sizeof...(args) == 0) std::snprintf(buf, sizeof buf, "%s", fmt);
+  else std::snprintf(buf, sizeof buf, fmt, args...);
+  throw exception(buf);
+}
+
+// external pointers: SEXP is an opaque handle; XPtr<T, Storage, Finalizer> wraps a T* (the finaliser runs when R
+// collects the object; here: never -- the harness destroys what it creates)
+}  // namespace Rcpp
+typedef void* SEXP;
+namespace Rcpp {
+template <typename T>
+struct PreserveStorage {};
+template <typename T>
+void standard_delete_finalizer(T* p) { delete p; }
+template <typename T, template <class> class Storage = PreserveStorage, void Finalizer(T*) = standard_delete_finalizer<T>,
+          bool finalizeOnExit = false>
+struct XPtr {
+  T* p;
+  explicit XPtr(T* ptr, bool set_delete_finalizer = true) : p(ptr) { (void)set_delete_finalizer; }
+  XPtr(SEXP s) : p(static_cast<T*>(s)) {}
+  operator SEXP() const { return static_cast<SEXP>(p); }
+  T* get() const { return p; }
+  T* operator->() const { return p; }
+};
 
 }  // namespace Rcpp

@@ -29,7 +29,7 @@ for k in range(nt):
           f"{us(F[0], F[1]):7.2f} {us(F[1], F[2]):7.2f}   at {us(t0, T[0]):8.2f}")
 lv = t[nt]
 end = None
-print("inverse levels (own stage 1, barrier, own stage 2, barrier):")
+print("end of kernel (output layout written):")
 flat = np.concatenate([t[nt], t[nt + 1], t[nt + 2]])
 prev = t[nt - 1, 3]
 for i, v in enumerate(flat):
@@ -38,7 +38,3 @@ for i, v in enumerate(flat):
     print(f"  stamp {i}: +{(v - prev) / GHZ / 1e3:7.2f} us   at {(v - t0) / GHZ / 1e3:8.2f}")
     prev = v
 
-pc = np.array(buf[240:246], dtype=np.int64)
-pt = np.array(buf[280:287], dtype=np.int64)
-print("chol tile 0 probes (cycles): load->", np.diff(pc).tolist(), " = cols 0-3 | 4-7 | 8-15 | 16-31 | L out")
-print("trsm tile (1,0) probes (cycles):", np.diff(pt).tolist(), " = load factor | cols 0-7 | 8-15 | 16-23 | 24-31 | store")
