@@ -145,12 +145,20 @@ static int launch_kernmat(const KernArgs& a, int kind, cudaStream_t st) {
   } else {
     grid = (unsigned)((a.n1_pad / kb::T) * (a.n2_pad / kb::T));
   }
+  auto go = [&](auto kern) -> int {
+    ACE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, st>>>(a);
+    return 0;
+  };
+  const int bc = kb::chunk_terms(B);  // terms per chunk x columns per step: 16 or 24 accumulators per thread
   if (kind == 0) {
-    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernmat_kernel<0><<<grid, 256, smem, st>>>(a);
+    if (bc == 4) ACE_TRY(go(kernmat_kernel<0, 4, 4>));
+    else if (bc == 8) ACE_TRY(go(kernmat_kernel<0, 8, 2>));
+    else ACE_TRY(go(kernmat_kernel<0, 12, 2>));
   } else {
-    ACE_CUDA(cudaFuncSetAttribute(kernmat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernmat_kernel<1><<<grid, 256, smem, st>>>(a);
+    if (bc == 4) ACE_TRY(go(kernmat_kernel<1, 4, 4>));
+    else if (bc == 8) ACE_TRY(go(kernmat_kernel<1, 8, 2>));
+    else ACE_TRY(go(kernmat_kernel<1, 12, 2>));
   }
   ACE_CUDA(cudaGetLastError());
   return 0;
@@ -160,6 +168,7 @@ struct GradPlan {
   int PD = 0, BT = 0, groups = 0, gy = 0, threads = 0, gx = 0;
   size_t smem = 0;
   int v2 = 0, PD8 = 0, BD8 = 0;  // second-generation kernel (grad2_kernel.cuh) when the shape is instantiated
+  int nw2 = 8;                   // its warps per CTA: 8 (<= 255 registers) or 16 (128 registers)
 };
 
 static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
@@ -193,28 +202,37 @@ static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
   // grad2_kernel: one thread per pair for all terms, length-scale sums on the tensor pipe
   const int PD8 = (p + 7) / 8 * 8, BD8 = (B + 7) / 8 * 8;
   const char* impl = std::getenv("ACE_GRAD_IMPL");
-  // measured (profiles/r01): grad2 wins for p <= 16 (C2: 0.76 vs 0.88 ms), grad_kernel for p = 20 (C3: 18.9 vs 19.6 ms)
-  const bool want2 = impl ? (std::atoi(impl) == 2) : (p <= 16);
+  // measured (profiles/r02/grad_sweep2.log, gemv + gradient + finalize phase, ms): with 16 warps per CTA at 128
+  // registers grad2 wins at every BASELINE shape -- C3 (n=8192) 4.91 -> 4.51, C2 0.90 -> 0.61, C5 1.68 -> 1.33,
+  // C4 (n=8192) 2.27 -> 1.23; with 8 warps (<= 255 registers) it only won for p <= 16 (profiles/r01)
+  const bool want2 = impl ? (std::atoi(impl) == 2) : true;
   if (PD8 <= 32 && BD8 <= 16 && want2) {
-    const size_t sm2 = g2::smem_bytes(PD8, BD8, B - 1);
+    int nw = 16;
+    if (const char* e = std::getenv("ACE_GRAD2_WARPS")) nw = (std::atoi(e) == 8) ? 8 : 16;
+    size_t sm2 = g2::smem_bytes(PD8, BD8, B - 1, nw, kind);
+    if (sm2 > 227 * 1024 && nw == 16) {
+      nw = 8;
+      sm2 = g2::smem_bytes(PD8, BD8, B - 1, nw, kind);
+    }
     if (sm2 <= 227 * 1024) {
-      pl->v2 = 1; pl->PD8 = PD8; pl->BD8 = BD8; pl->smem = sm2; pl->gy = 1; pl->threads = 256;
+      pl->v2 = 1; pl->PD8 = PD8; pl->BD8 = BD8; pl->smem = sm2; pl->gy = 1; pl->threads = 32 * nw; pl->nw2 = nw;
     }
   }
   return 0;
 }
 
-template <int PD8, int BD8>
-static int launch_grad2_t(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
-  if (kind == 0) {
-    ACE_CUDA(cudaFuncSetAttribute(grad2_kernel<PD8, BD8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    grad2_kernel<PD8, BD8, 0><<<pl.gx, 256, pl.smem, st>>>(a);
-  } else {
-    ACE_CUDA(cudaFuncSetAttribute(grad2_kernel<PD8, BD8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    grad2_kernel<PD8, BD8, 1><<<pl.gx, 256, pl.smem, st>>>(a);
-  }
+template <int PD8, int BD8, int KIND, int NW>
+static int launch_grad2_k(const GradArgs& a, const GradPlan& pl, cudaStream_t st) {
+  ACE_CUDA(cudaFuncSetAttribute(grad2_kernel<PD8, BD8, KIND, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  grad2_kernel<PD8, BD8, KIND, NW><<<pl.gx, NW * 32, pl.smem, st>>>(a);
   ACE_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int PD8, int BD8>
+static int launch_grad2_t(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
+  if (pl.nw2 == 16) return kind == 0 ? launch_grad2_k<PD8, BD8, 0, 16>(a, pl, st) : launch_grad2_k<PD8, BD8, 1, 16>(a, pl, st);
+  return kind == 0 ? launch_grad2_k<PD8, BD8, 0, 8>(a, pl, st) : launch_grad2_k<PD8, BD8, 1, 8>(a, pl, st);
 }
 
 static int launch_grad2(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {

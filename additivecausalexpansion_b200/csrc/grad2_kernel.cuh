@@ -19,17 +19,22 @@ namespace g2 {
 constexpr int T = 64;      // tile edge
 constexpr int LDS_ = 36;   // stage row stride (32 pairs + 4): conflict-free DMMA fragment loads
 inline int wstride(int B) { return 2 * ((B + 2) / 2); }  // >= B + 1, even
-inline size_t smem_bytes(int PD8, int BD8, int Bz) {
+// nwarps: 8 (256 threads, up to 255 registers) or 16 (512 threads, 128 registers: twice the warps per scheduler to
+// cover the fixed-latency FP64 dependencies -- ncu r02: 2 warps per scheduler issue 0.47 IPC, FP64 pipe 52 %).
+// kind 1 (Matern) does not use log|z|: its tiles are not staged.
+inline size_t smem_bytes(int PD8, int BD8, int Bz, int nwarps = 8, int kind = 0) {
   const int B = Bz + 1;
-  size_t d = (size_t)2 * PD8 * T + (size_t)4 * Bz * T + 2 * T + (size_t)PD8 * wstride(B) + BD8 +
-             (size_t)8 * (BD8 + PD8) * LDS_;
+  size_t d = (size_t)2 * PD8 * T + (size_t)(kind ? 2 : 4) * Bz * T + 2 * T + (size_t)PD8 * wstride(B) + BD8 +
+             (size_t)nwarps * (BD8 + PD8) * LDS_;
   return d * 8 + 16;
 }
 }  // namespace g2
 
-template <int PD8, int BD8, int KIND>
-__global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
+template <int PD8, int BD8, int KIND, int NWARPS = 8>
+__global__ void __launch_bounds__(NWARPS * 32, 1) grad2_kernel(const GradArgs a) {
   using namespace g2;
+  constexpr int NTHR = NWARPS * 32;
+  constexpr int JCOLS = 128 / NWARPS;  // columns of the 64 x 64 tile per warp: 16 (8 warps) or 8 (16 warps)
   constexpr int MT = BD8 / 8, NT = PD8 / 8;
   constexpr int NE = BD8 + 1;  // distance sums kept per thread (c = 0..B, B <= BD8)
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -40,32 +45,32 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
   double* Xj = Xi + PD8 * T;
   double* Zi = Xj + PD8 * T;
   double* Zj = Zi + Bz * T;
-  double* LZi = Zj + Bz * T;
-  double* LZj = LZi + Bz * T;
-  double* ai = LZj + Bz * T;
+  double* LZi = Zj + Bz * T;                      // Matern: not staged (term_value<1> does not read log|z|)
+  double* LZj = LZi + (KIND ? 0 : Bz * T);
+  double* ai = LZj + (KIND ? 0 : Bz * T);
   double* aj = ai + T;
   double* wt_s = aj + T;            // [PD8][WS] extended weight table rows (columns 0..B)
   double* lam = wt_s + PD8 * WS;    // [BD8]
-  double* stage = lam + BD8;        // [8 warps][(BD8 + PD8)][LDS_]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 8 * (BD8 + PD8) * LDS_);
+  double* stage = lam + BD8;        // [NWARPS][(BD8 + PD8)][LDS_]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + NWARPS * (BD8 + PD8) * LDS_);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   const int li = (warp & 1) * 32 + lane;   // row of the tile owned by this thread
-  const int jbase = (warp >> 1) * 16;      // this warp's 16 columns of the tile
+  const int jbase = (warp >> 1) * JCOLS;   // this warp's columns of the tile
   double* Ts = stage + warp * (BD8 + PD8) * LDS_;  // [BD8][LDS_]  t_b of the warp's 32 pairs
   double* Ds = Ts + BD8 * LDS_;                    // [PD8][LDS_]  D^2_d of the warp's 32 pairs
 
-  for (int idx = threadIdx.x; idx < PD8 * WS; idx += 256) {
+  for (int idx = threadIdx.x; idx < PD8 * WS; idx += NTHR) {
     const int d = idx / WS, c = idx % WS;
     wt_s[idx] = (d < p && c <= B) ? a.tab[TAB_WE + d * WSTRIDE + c] : 0.0;
   }
-  for (int b = threadIdx.x; b < BD8; b += 256) lam[b] = (b < B) ? a.tab[TAB_LAM + b] : 0.0;
-  for (int idx = threadIdx.x; idx < (PD8 - p) * T; idx += 256) {  // padded d rows stay zero (TMA never writes them)
+  for (int b = threadIdx.x; b < BD8; b += NTHR) lam[b] = (b < B) ? a.tab[TAB_LAM + b] : 0.0;
+  for (int idx = threadIdx.x; idx < (PD8 - p) * T; idx += NTHR) {  // padded d rows stay zero (TMA never writes them)
     Xi[p * T + idx] = 0.0;
     Xj[p * T + idx] = 0.0;
   }
-  for (int idx = threadIdx.x; idx < 8 * (BD8 + PD8) * LDS_; idx += 256) stage[idx] = 0.0;  // rows b >= B stay zero
+  for (int idx = threadIdx.x; idx < NWARPS * (BD8 + PD8) * LDS_; idx += NTHR) stage[idx] = 0.0;  // rows b >= B stay zero
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
 
     __syncthreads();  // previous tile fully consumed before the TMA overwrites the staging tiles
     if (warp == 0) {
-      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)((2 * p + 4 * Bz + 2) * T * 8));
+      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)((2 * p + (KIND ? 2 : 4) * Bz + 2) * T * 8));
       __syncwarp();
       for (int c = lane; c < p; c += 32) {
         tma_bulk_g2s(Xi + c * T, a.X + i0 + (size_t)c * a.ldx, T * 8, bar);
@@ -101,8 +106,10 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
       for (int c = lane; c < Bz; c += 32) {
         tma_bulk_g2s(Zi + c * T, a.Z + i0 + (size_t)c * a.ldx, T * 8, bar);
         tma_bulk_g2s(Zj + c * T, a.Z + j0 + (size_t)c * a.ldx, T * 8, bar);
-        tma_bulk_g2s(LZi + c * T, a.LZ + i0 + (size_t)c * a.ldx, T * 8, bar);
-        tma_bulk_g2s(LZj + c * T, a.LZ + j0 + (size_t)c * a.ldx, T * 8, bar);
+        if (KIND == 0) {
+          tma_bulk_g2s(LZi + c * T, a.LZ + i0 + (size_t)c * a.ldx, T * 8, bar);
+          tma_bulk_g2s(LZj + c * T, a.LZ + j0 + (size_t)c * a.ldx, T * 8, bar);
+        }
       }
       if (lane == 0) {
         tma_bulk_g2s(ai, a.alpha + i0, T * 8, bar);
@@ -118,11 +125,11 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
     double rowacc = 0.0;
     double knext = kcol[0];
 #pragma unroll 1
-    for (int jc = 0; jc < 16; ++jc) {
+    for (int jc = 0; jc < JCOLS; ++jc) {
       const int jj = jbase + jc;
       const int gj = j0 + jj;
       const double kinv = knext;
-      if (jc + 1 < 16) knext = kcol[(size_t)(jc + 1) * a.ld];
+      if (jc + 1 < JCOLS) knext = kcol[(size_t)(jc + 1) * a.ld];
       const double alpha_j = aj[jj];
       const bool valid = (gi < a.n) && (gj < a.n);
       const double W = valid ? wt * (kinv - alpha_i * alpha_j) : 0.0;
@@ -166,8 +173,10 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
           if (b > 0) {
             zi = Zi[(b - 1) * T + li];
             zj = Zj[(b - 1) * T + jj];
-            lzi = LZi[(b - 1) * T + li];
-            lzj = LZj[(b - 1) * T + jj];
+            if (KIND == 0) {
+              lzi = LZi[(b - 1) * T + li];
+              lzj = LZj[(b - 1) * T + jj];
+            }
           }
           const double kv = term_value<KIND>(b, lam[b], E[b], zj, zi, lzj, lzi);
           kpart += kv;
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
   // ---- CTA reduction: per-warp fragments / lane sums -> smem -> one partial row per CTA -------------
   constexpr int NV = BD8 * PD8 + BD8;
   __syncthreads();           // everybody is done with the stage buffers; reuse them as red[8][NV]
-  double* red = stage;       // 8 * NV <= 8 * (BD8 + PD8) * 36 for every instantiated shape (checked on host)
+  double* red = stage;       // NWARPS * NV <= NWARPS * (BD8 + PD8) * 36 for every instantiated shape (checked on host)
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -218,12 +227,12 @@ __global__ void __launch_bounds__(256, 1) grad2_kernel(const GradArgs a) {
   }
   __syncthreads();
   double* out = a.partials + (size_t)blockIdx.x * a.P;
-  for (int idx = threadIdx.x; idx < a.P; idx += 256) out[idx] = 0.0;
+  for (int idx = threadIdx.x; idx < a.P; idx += NTHR) out[idx] = 0.0;
   __syncthreads();
-  for (int r = threadIdx.x; r < NV; r += 256) {
+  for (int r = threadIdx.x; r < NV; r += NTHR) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += red[w * NV + r];
+    for (int w = 0; w < NWARPS; ++w) v += red[w * NV + r];
     if (r < BD8 * PD8) {
       const int b = r / PD8, d = r % PD8;
       if (d < p && b < B) out[2 + B + b + B * d] = v;

@@ -67,8 +67,13 @@ struct KernArgs {
 namespace kb {
 constexpr int T = 64;        // tile edge
 constexpr int LDT = T + 1;   // staging tile stride
-constexpr int BC = 4;        // additive terms per chunk
-inline int bpad(int B) { return (B + BC - 1) / BC * BC; }
+// additive terms per chunk: every chunk re-derives D^2_d from the staged X tiles, so ONE chunk for B <= 12 (C3: B = 12,
+// C2: B = 8) instead of three / two chunks of 4 saves 2 * (chunks - 1) FP64 instructions per pair and dimension
+inline int chunk_terms(int B) { return B <= 4 ? 4 : (B <= 8 ? 8 : 12); }
+inline int bpad(int B) {
+  const int bc = chunk_terms(B);
+  return (B + bc - 1) / bc * bc;
+}
 inline size_t smem_bytes(int p, int Bz, bool sym) {
   const int B = Bz + 1;
   size_t d = (size_t)(2 * p + 4 * Bz) * T + (size_t)p * bpad(B) + bpad(B) + (sym ? (size_t)T * LDT : 0);
@@ -76,7 +81,8 @@ inline size_t smem_bytes(int p, int Bz, bool sym) {
 }
 }  // namespace kb
 
-template <int KIND>
+// BC additive terms per chunk, QC columns per step (BC * QC accumulators per thread)
+template <int KIND, int BC, int QC>
 __global__ void __launch_bounds__(256, 2) kernmat_kernel(const KernArgs a) {
   using namespace kb;
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -140,34 +146,36 @@ __global__ void __launch_bounds__(256, 2) kernmat_kernel(const KernArgs a) {
   const int li = threadIdx.x & 63, cg = threadIdx.x >> 6;
   const int gi = i0 + li;
 #pragma unroll 1
-  for (int step = 0; step < 4; ++step) {
-    const int jj0 = cg * 16 + step * 4;
-    double ksum[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int step = 0; step < 16 / QC; ++step) {
+    const int jj0 = cg * 16 + step * QC;
+    double ksum[QC];
+#pragma unroll
+    for (int q = 0; q < QC; ++q) ksum[q] = 0.0;
 #pragma unroll 1
     for (int b0 = 0; b0 < B; b0 += BC) {
-      double acc[4][BC];
+      double acc[QC][BC];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < QC; ++q)
 #pragma unroll
         for (int t = 0; t < BC; ++t) acc[q][t] = 0.0;
 #pragma unroll 4
       for (int d = 0; d < p; ++d) {
         const double xi = Xi[d * T + li];
-        const double2 xa = *reinterpret_cast<const double2*>(Xj + d * T + jj0);
-        const double2 xb = *reinterpret_cast<const double2*>(Xj + d * T + jj0 + 2);
-        double d2[4];
-        d2[0] = (xi - xa.x) * (xi - xa.x);
-        d2[1] = (xi - xa.y) * (xi - xa.y);
-        d2[2] = (xi - xb.x) * (xi - xb.x);
-        d2[3] = (xi - xb.y) * (xi - xb.y);
-        const double2 w01 = *reinterpret_cast<const double2*>(wb + d * BP + b0);
-        const double2 w23 = *reinterpret_cast<const double2*>(wb + d * BP + b0 + 2);
+        double d2[QC];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          acc[q][0] = fma(d2[q], w01.x, acc[q][0]);
-          acc[q][1] = fma(d2[q], w01.y, acc[q][1]);
-          acc[q][2] = fma(d2[q], w23.x, acc[q][2]);
-          acc[q][3] = fma(d2[q], w23.y, acc[q][3]);
+        for (int q = 0; q < QC; q += 2) {
+          const double2 xa = *reinterpret_cast<const double2*>(Xj + d * T + jj0 + q);
+          d2[q] = (xi - xa.x) * (xi - xa.x);
+          d2[q + 1] = (xi - xa.y) * (xi - xa.y);
+        }
+#pragma unroll
+        for (int t = 0; t < BC; t += 2) {
+          const double2 w = *reinterpret_cast<const double2*>(wb + d * BP + b0 + t);
+#pragma unroll
+          for (int q = 0; q < QC; ++q) {
+            acc[q][t] = fma(d2[q], w.x, acc[q][t]);
+            acc[q][t + 1] = fma(d2[q], w.y, acc[q][t + 1]);
+          }
         }
       }
 #pragma unroll
@@ -181,7 +189,7 @@ __global__ void __launch_bounds__(256, 2) kernmat_kernel(const KernArgs a) {
             lzi = LZi[(b - 1) * T + li];
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < QC; ++q) {
             const int jj = jj0 + q, gj = j0 + jj;
             double zj = 1.0, lzj = 0.0;
             if (b > 0) {
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(256, 2) kernmat_kernel(const KernArgs a) {
       }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < QC; ++q) {
       const int jj = jj0 + q, gj = j0 + jj;
       if (a.sym) {
         Tt[li * LDT + jj] = ksum[q];
