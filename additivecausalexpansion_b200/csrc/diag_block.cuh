@@ -173,7 +173,7 @@ __device__ __noinline__ void dg_tile_gemm(double* stage, int lane, const double*
 // ---------------------------------------------------------------------------------------------
 template <int JB, int H>
 __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, double* colbuf, double* dg_, double* idg,
-                                             int tx, int ty, int* info, int gidx0) {
+                                             int tx, int ty, int* info, int gidx0, volatile int* progress, int base) {
   constexpr int A0 = 2 * JB + H;  // row block of the pivots of these 4 columns
 #pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
@@ -184,6 +184,10 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, doub
       for (int a = A0; a < 8; ++a) cb[4 * a + ty] = r[a][JB];
     }
     __syncwarp();
+    if (tx == 0 && ty == 0 && j > 0) {  // columns < j of L and their 1/L_jj are in shared memory: the follower may go on
+      __threadfence_block();
+      *progress = base + j;
+    }
     const double pj = cb[j];
     // one MUFU-seeded reciprocal square root serves the whole column: 1/L_jj = y, L_jj = p y, 1/p = y^2
     const double inv = fast_rsqrt(pj);
@@ -202,17 +206,15 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, doub
     // the column of L leaves AFTER the update was issued: it is off the critical path (the owners' copy of column j
     // is untouched by the update: their cm[JB] is masked to zero)
     if (tx == jx) {
+      if (ty > jj) Ls[4 * A0 + ty + j * 33] = r[A0][JB] * inv;  // the pivot's row block: rows below the pivot only
 #pragma unroll
-      for (int a = A0; a < 8; ++a) {
-        const int i = 4 * a + ty;
-        if (i > j) Ls[i + j * 33] = r[a][JB] * inv;
-        if (i == j) {
-          double sq = pj * inv;
-          sq = fma(fma(-sq, sq, pj), 0.5 * inv, sq);
-          dg_[j] = sq;
-          idg[j] = inv;
-          if (!(pj > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
-        }
+      for (int a = A0 + 1; a < 8; ++a) Ls[4 * a + ty + j * 33] = r[a][JB] * inv;
+      if (ty == jj) {  // the pivot itself (one lane): L_jj by one Newton step on p y, 1 / L_jj, positivity check
+        double sq = pj * inv;
+        sq = fma(fma(-sq, sq, pj), 0.5 * inv, sq);
+        dg_[j] = sq;
+        idg[j] = inv;
+        if (!(pj > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
       }
     }
   }
@@ -222,12 +224,15 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, doub
 // r(i, :) -= L(i, j) X(j, :) for i > j.  X(j, k), k < j goes to the upper triangle of Ls as U(k, j).
 template <int A>
 __device__ __forceinline__ void dg_inv_rows(double (&r)[8][4], double* Ls, double* rowbuf, const double* idg, int tx,
-                                            int ty) {
+                                            int ty, const volatile int* progress, int base) {
   constexpr int BMAX = A / 2;  // column blocks 0 .. BMAX hold the columns k <= j
 #pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
     const int j = 4 * A + jj;
     double* rb = rowbuf + (j & 1) * 32;
+    while (*progress < base + j + 1) {  // column j of L published by the factoring warp?
+    }
+    __threadfence_block();
     if (ty == jj) {
       const double dj = idg[j];
 #pragma unroll
@@ -255,28 +260,35 @@ __device__ __forceinline__ void dg_inv_rows(double (&r)[8][4], double* Ls, doubl
   }
 }
 
-// Writes L (lower of At), diag(L) -> dv, X = L^-1 (lower) and U = X^T (upper) -> St (full 32 x 32 tile).
-__device__ __noinline__ void dg_factor_tile(double* sm, int lane, double* At, long ld, double* St, long lds,
-                                            double* dv, int* info, int gidx0) {
-  double* Ls = sm;                 // [32][33]: strictly lower = L, strictly upper = U (filled by the inverse)
-  double* colbuf = sm + 32 * 33;   // 2 x 32: pivot column / row, double buffered
-  double* dgl = colbuf + 64;       // L_jj
-  double* idg = dgl + 32;          // 1 / L_jj
+// The diagonal tile is factored by TWO warps of one CTA: the leader runs the Cholesky (and writes L, diag(L)), the
+// follower computes X = L^-1 one column behind it -- row j of X only needs columns <= j of L -- and writes the X / U
+// tile.  Both work on the leader's shared-memory stage `sm0` (columns of L below the diagonal, rows of U above it);
+// `progress` counts the columns the leader has published, monotonically over the tiles this CTA factors.
+__device__ __noinline__ void dg_chol_lead(double* sm0, int lane, double* At, long ld, double* dv, int* info, int gidx0,
+                                          volatile int* progress, int base) {
+  double* Ls = sm0;                 // [32][33]: strictly lower = L, strictly upper = U (filled by the follower)
+  double* colbuf = sm0 + 32 * 33;   // 2 x 32: pivot column, double buffered
+  double* dgl = colbuf + 64;        // L_jj
+  double* idg = dgl + 32;           // 1 / L_jj
   const int tx = lane & 7, ty = lane >> 3;
   double r[8][4];
 #pragma unroll
   for (int b = 0; b < 4; ++b)
 #pragma unroll
     for (int a = 0; a < 8; ++a) r[a][b] = __ldcg(At + (4 * a + ty) + (size_t)(8 * b + tx) * ld);
-  dg_chol_cols<0, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  dg_chol_cols<0, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  dg_chol_cols<1, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  dg_chol_cols<1, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  dg_chol_cols<2, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  dg_chol_cols<2, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  dg_chol_cols<3, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
-  dg_chol_cols<3, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0);
+  dg_chol_cols<0, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+  dg_chol_cols<0, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+  dg_chol_cols<1, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+  dg_chol_cols<1, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+  dg_chol_cols<2, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+  dg_chol_cols<2, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+  dg_chol_cols<3, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+  dg_chol_cols<3, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
   __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    *progress = base + 32;
+  }
   // L out: column c, lane = row (coalesced)
 #pragma unroll 4
   for (int c = 0; c < 32; ++c) {
@@ -284,18 +296,28 @@ __device__ __noinline__ void dg_factor_tile(double* sm, int lane, double* At, lo
     if (lane == c) __stcg(At + lane + (size_t)c * ld, dgl[c]);
   }
   dv[lane] = dgl[lane];
+  __syncwarp();
+}
+
+__device__ __noinline__ void dg_inv_follow(double* sm0, double* sm_own, int lane, double* St, long lds,
+                                           const volatile int* progress, int base) {
+  double* Ls = sm0;
+  const double* idg = sm0 + 32 * 33 + 96;
+  double* rowbuf = sm_own;  // 2 x 32 in the follower's own stage
+  const int tx = lane & 7, ty = lane >> 3;
+  double r[8][4];
 #pragma unroll
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) r[a][b] = (4 * a + ty == 8 * b + tx) ? 1.0 : 0.0;
-  dg_inv_rows<0>(r, Ls, colbuf, idg, tx, ty);
-  dg_inv_rows<1>(r, Ls, colbuf, idg, tx, ty);
-  dg_inv_rows<2>(r, Ls, colbuf, idg, tx, ty);
-  dg_inv_rows<3>(r, Ls, colbuf, idg, tx, ty);
-  dg_inv_rows<4>(r, Ls, colbuf, idg, tx, ty);
-  dg_inv_rows<5>(r, Ls, colbuf, idg, tx, ty);
-  dg_inv_rows<6>(r, Ls, colbuf, idg, tx, ty);
-  dg_inv_rows<7>(r, Ls, colbuf, idg, tx, ty);
+  dg_inv_rows<0>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<1>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<2>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<3>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<4>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<5>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<6>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<7>(r, Ls, rowbuf, idg, tx, ty, progress, base);
   __syncwarp();
   // X (lower) / U (upper) tile out: column c, lane = row.  X(i, c) = U(c, i) = Ls[c + i * 33] for i > c.
 #pragma unroll 4
@@ -318,10 +340,13 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
   if (lane == 0) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * TS * LDT);
     mbar_init(bar, 1);
-    *reinterpret_cast<uint32_t*>(bar + 1) = 0u;
+    reinterpret_cast<uint32_t*>(bar + 1)[0] = 0u;  // phase of the warp's mbarrier
+    reinterpret_cast<uint32_t*>(bar + 1)[1] = 0u;  // warp 0 only: columns of L published to the follower (see below)
     fence_mbar_init();
   }
   __syncthreads();
+  double* stage0 = reinterpret_cast<double*>(smraw);  // warp 0's stage: the tile factorisation lives there
+  volatile int* progress = reinterpret_cast<volatile int*>(stage0 + 2 * TS * LDT + 1) + 1;
   const int nt = a.nblk * 4;            // 32-tiles per side
   const long N = (long)nt * TS;
   const long ld = a.ld;
@@ -341,7 +366,7 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
   };
 
   // ------------------------------------------------------------------ factorisation + inverse, interleaved
-  // Serial chain per tile column k:  Cholesky + inverse of the diagonal tile (one warp) -> barrier -> column solve
+  // Serial chain per tile column k:  Cholesky of the diagonal tile (its inverse follows on a second warp) -> barrier -> column solve
   // L_ik = A_ik X_kk^T (every warp one tile product) -> barrier -> update of the next diagonal tile (the warp that will
   // factor it).  Everything else hides behind it:
   //   * trailing update A_ij -= L_ik L_jk^T, dealt over the warps of the other CTAs;
@@ -352,10 +377,13 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
   // (Measured alternatives, profiles/r02/diag_block_timeline.md: a bottom-up merge tree after the factorisation
   // costs +140 us; solving the column by substitution against L_kk with X_kk computed one slot later takes the tile
   // inverse off the chain but the rolled substitution is slower than the tile product: 433 vs 379 us per block.)
+  // tile k is factored by warp 0 (Cholesky) and warp 1 (inverse, one column behind) of CTA k mod NC
   if (gw == fw(0)) {
     stampF(0, 1);
-    dg_factor_tile(stage, lane, At(0, 0), ld, St(0, 0), N, dv, a.info, a.blk0 * 128);
+    dg_chol_lead(stage0, lane, At(0, 0), ld, dv, a.info, a.blk0 * 128, progress, 0);
     stampF(0, 2);
+  } else if (gw == fw(0) + NC) {
+    dg_inv_follow(stage0, stage, lane, St(0, 0), N, progress, 0);
   }
 #pragma unroll 1
   for (int k = 0; k < nt; ++k) {
@@ -392,9 +420,11 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
                    At(k + 1, k + 1), ld, nullptr, 0);
       __syncwarp();
       stampF(k + 1, 1);
-      dg_factor_tile(stage, lane, At(k + 1, k + 1), ld, St(k + 1, k + 1), N, dv + (k + 1) * TS, a.info,
-                     a.blk0 * 128 + (k + 1) * TS);
+      dg_chol_lead(stage0, lane, At(k + 1, k + 1), ld, dv + (k + 1) * TS, a.info, a.blk0 * 128 + (k + 1) * TS, progress,
+                   32 * ((k + 1) / NC));
       stampF(k + 1, 2);
+    } else if (gw == f + NC) {  // warp 1 of the factoring CTA
+      dg_inv_follow(stage0, stage, lane, St(k + 1, k + 1), N, progress, 32 * ((k + 1) / NC));
     } else if (crank != f) {
       constexpr int NWK = (NC - 1) * WARPS;                        // worker warps
       const int me = warp * (NC - 1) + (crank - f - 1 + NC) % NC;  // 0 .. NWK-1, CTA index fastest
