@@ -38,11 +38,11 @@ class AceFitConfig(C.Structure):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/ace_b200.cu into libace_b200.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu into libace_b200.so (nvcc cross-compiles without a GPU; objects build in parallel)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl"))] + [HEADER]
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
     if force or stale:
-        cmd = ["make", "-C", CSRC, "../libace_b200.so"] + (["-B"] if force else [])
+        cmd = ["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC, "../libace_b200.so"] + (["-B"] if force else [])
         subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     return SO_PATH
 

@@ -19,6 +19,7 @@
 #include "gp_kernels.cuh"
 #include "pair_kernels.cuh"
 #include "grad2_kernel.cuh"
+#include "grad3_kernel.cuh"
 #include "pred_kernels.cuh"
 
 namespace ace {
@@ -169,7 +170,18 @@ struct GradPlan {
   size_t smem = 0;
   int v2 = 0, PD8 = 0, BD8 = 0;  // second-generation kernel (grad2_kernel.cuh) when the shape is instantiated
   int nw2 = 8;                   // its warps per CTA: 8 (<= 255 registers) or 16 (128 registers)
+  int v3 = 0, NT3 = 0;           // third-generation kernel (grad3_kernel.cuh, exact-shape instantiations in pair_grad3.cu)
 };
+
+// launchers exported by the pair_grad3.cu objects (one per kernel kind and p tile count)
+int launch_grad3_k0_nt1(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k0_nt2(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k0_nt3(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k0_nt4(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k1_nt1(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k1_nt2(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k1_nt3(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k1_nt4(const GradArgs&, int, size_t, cudaStream_t);
 
 static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
   static const int table[][2] = {{4, 16}, {8, 8}, {12, 5}, {16, 4}, {20, 3}, {24, 2}, {32, 2}, {48, 1}, {64, 1}};
@@ -205,7 +217,17 @@ static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
   // measured (profiles/r02/grad_sweep2.log, gemv + gradient + finalize phase, ms): with 16 warps per CTA at 128
   // registers grad2 wins at every BASELINE shape -- C3 (n=8192) 4.91 -> 4.51, C2 0.90 -> 0.61, C5 1.68 -> 1.33,
   // C4 (n=8192) 2.27 -> 1.23; with 8 warps (<= 255 registers) it only won for p <= 16 (profiles/r01)
-  const bool want2 = impl ? (std::atoi(impl) == 2) : true;
+  const int want = impl ? std::atoi(impl) : 3;
+  const bool want2 = want >= 2;
+  // grad3_kernel: the same decomposition with the exact number of terms compiled in and lock-step exp / sqrt / rcp
+  if (want == 3 && p <= 32 && B <= 16) {
+    const int NT = (p + 7) / 8;
+    const size_t sm3 = g3::smem_bytes(NT, B, kind, 16);
+    if (sm3 <= 227 * 1024) {
+      pl->v3 = 1; pl->NT3 = NT; pl->smem = sm3; pl->gy = 1; pl->threads = 512;
+      return 0;
+    }
+  }
   if (PD8 <= 32 && BD8 <= 16 && want2) {
     int nw = 16;
     if (const char* e = std::getenv("ACE_GRAD2_WARPS")) nw = (std::atoi(e) == 8) ? 8 : 16;
@@ -266,6 +288,18 @@ static int launch_grad_t(const GradArgs& a, int kind, const GradPlan& pl, cudaSt
 static int launch_grad2(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st);
 
 static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
+  if (pl.v3) {
+    switch (kind * 10 + pl.NT3) {
+      case 1: return launch_grad3_k0_nt1(a, pl.gx, pl.smem, st);
+      case 2: return launch_grad3_k0_nt2(a, pl.gx, pl.smem, st);
+      case 3: return launch_grad3_k0_nt3(a, pl.gx, pl.smem, st);
+      case 4: return launch_grad3_k0_nt4(a, pl.gx, pl.smem, st);
+      case 11: return launch_grad3_k1_nt1(a, pl.gx, pl.smem, st);
+      case 12: return launch_grad3_k1_nt2(a, pl.gx, pl.smem, st);
+      case 13: return launch_grad3_k1_nt3(a, pl.gx, pl.smem, st);
+      default: return launch_grad3_k1_nt4(a, pl.gx, pl.smem, st);
+    }
+  }
   if (pl.v2) return launch_grad2(a, kind, pl, st);
   switch (pl.PD) {
     case 4: return launch_grad_t<4, 16>(a, kind, pl, st);

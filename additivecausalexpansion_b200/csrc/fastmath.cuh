@@ -16,7 +16,7 @@ namespace ace {
 // through the read-only path: the index differs per lane) and a degree-5 Taylor polynomial (r^6/720 < 4e-17) instead
 // of a degree-12 one on |r| <= ln2/2 -- 11 FP64 instructions instead of 18 per call, and the pair kernels are bound by
 // the FP64 pipe.  Error <= 1.4 ulp (checked against mpmath over [-700, 700]).
-__device__ const double kExp2Tab[64] = {
+static __device__ const double kExp2Tab[64] = {
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
     1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
     1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
@@ -33,7 +33,7 @@ __device__ const double kExp2Tab[64] = {
     1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
-__constant__ double kExpC[12] = {
+static __constant__ double kExpC[12] = {
     8.333333333333333e-03,   // 1/5!
     4.1666666666666664e-02,  // 1/4!
     1.6666666666666666e-01,  // 1/3!
@@ -95,6 +95,96 @@ __device__ __forceinline__ double fast_sqrt(double x) {
   double s = x * y;
   s = fma(fma(-s, s, x), 0.5 * y, s);
   return (x > 1e-290) ? s : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lock-step versions: N independent arguments advance one operation at a time, so that the instruction stream
+// carries N-fold instruction-level parallelism by construction.  The pair kernels run 4 warps per scheduler and a
+// dependent DFMA chain issues one instruction per 9 cycles (profiles/microbench/fp64_latency_r01.json); ncu r02 showed
+// the scalar versions above scheduled back to back (0.48 IPC, `wait` the top stall).
+// ---------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void fast_exp_n(double (&x)[N]) {  // x[k] <- exp(x[k]), same semantics as fast_exp
+  double xc[N], t[N], r[N], p[N], tb[N];
+  int n[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) xc[k] = (x[k] < -700.0) ? -700.0 : x[k];
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] = fma(xc[k], kExpC[6], kExpC[7]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    n[k] = __double2loint(t[k]);
+    tb[k] = __ldg(&kExp2Tab[n[k] & 63]);
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) t[k] -= kExpC[7];
+#pragma unroll
+  for (int k = 0; k < N; ++k) r[k] = fma(t[k], kExpC[4], xc[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) r[k] = fma(t[k], kExpC[5], r[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] = fma(kExpC[0], r[k], kExpC[1]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] = fma(p[k], r[k], kExpC[2]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] = fma(p[k], r[k], kExpC[3]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] = fma(p[k], r[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) p[k] *= tb[k];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double v = p[k] * __hiloint2double(((n[k] >> 6) + 1023) << 20, 0);
+    x[k] = (x[k] > 709.4) ? __longlong_as_double(0x7ff0000000000000LL) : v;
+  }
+}
+
+// x[k] <- 1 / x[k] for normal x: MUFU seed (~2^-23) + one cubic step (relative error ~2^-69 + rounding: <= 1 ulp)
+template <int N>
+__device__ __forceinline__ void fast_rcp_n(double (&x)[N]) {
+  double y[N], e[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(x[k]));
+#pragma unroll
+  for (int k = 0; k < N; ++k) e[k] = fma(-x[k], y[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) e[k] = fma(e[k], e[k], e[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) x[k] = fma(y[k], e[k], y[k]);
+}
+
+// x[k] <- sqrt(x[k]) for x >= 0 (exact 0 for x == 0).  REFINE adds the Newton step on the root that makes the result
+// correctly rounded in all but rare cases (kernel build: entries compared at 1e-12 absolute); without it the root
+// carries the rounding of two multiplications (<= 2 ulp), enough for the gradient pass.
+template <int N, bool REFINE>
+__device__ __forceinline__ void fast_sqrt_n(double (&x)[N]) {
+  double y[N], e[N], s[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(x[k]));
+#pragma unroll
+  for (int k = 0; k < N; ++k) e[k] = -x[k] * y[k];
+#pragma unroll
+  for (int k = 0; k < N; ++k) e[k] = fma(e[k], y[k], 1.0);
+#pragma unroll
+  for (int k = 0; k < N; ++k) s[k] = fma(0.375, e[k], 0.5);
+#pragma unroll
+  for (int k = 0; k < N; ++k) e[k] *= y[k];
+#pragma unroll
+  for (int k = 0; k < N; ++k) y[k] = fma(e[k], s[k], y[k]);
+#pragma unroll
+  for (int k = 0; k < N; ++k) s[k] = x[k] * y[k];
+  if (REFINE) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) e[k] = fma(-s[k], s[k], x[k]);
+#pragma unroll
+    for (int k = 0; k < N; ++k) y[k] *= 0.5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) s[k] = fma(e[k], y[k], s[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k) x[k] = (x[k] > 1e-290) ? s[k] : 0.0;
 }
 
 }  // namespace ace

@@ -18,22 +18,9 @@
 // The reference materialises the n x n x B cube; nothing here does (only the API-compat cube
 // output of kernmat_kernel, on request).
 #pragma once
-#include "common.cuh"
+#include "pair_common.cuh"
 
 namespace ace {
-
-constexpr int PMAX = 64;   // max confounder columns supported by the fused kernels
-constexpr int BMAXT = 32;  // max additive terms (B = Bz + 1)
-
-// derived-table layout (doubles) in the device buffer `tab`
-constexpr int TAB_ESIG = 0;                       // exp(theta[0])
-constexpr int TAB_LAM = 8;                        // lambda_b            [BMAXT]
-// Extended length-scale table we[d][c] = exp(-theta[1 + B + B*d + c]), c = 0..B  [PMAX][WSTRIDE].
-// The kernel BUILD reads the length-scale of (d, b) at theta[1 + b + B*(d+1)] = we[d][b] (quirk Q1), the
-// GRADIENT differentiates theta[2 + B + b + B*d] = we[d][b+1]: one table, shifted by one column.
-constexpr int WSTRIDE = 36;
-constexpr int TAB_WE = TAB_LAM + BMAXT;
-constexpr int TAB_SIZE = TAB_WE + PMAX * WSTRIDE;
 
 // scalar-slot layout (doubles) in the device buffer `sc`
 enum {
