@@ -170,18 +170,19 @@ struct GradPlan {
   size_t smem = 0;
   int v2 = 0, PD8 = 0, BD8 = 0;  // second-generation kernel (grad2_kernel.cuh) when the shape is instantiated
   int nw2 = 8;                   // its warps per CTA: 8 (<= 255 registers) or 16 (128 registers)
+  int cw3 = 1;                   // grad3: weights in __constant__ memory (0: shared memory; ACE_GRAD3_CW)
   int v3 = 0, NT3 = 0;           // third-generation kernel (grad3_kernel.cuh, exact-shape instantiations in pair_grad3.cu)
 };
 
 // launchers exported by the pair_grad3.cu objects (one per kernel kind and p tile count)
-int launch_grad3_k0_nt1(const GradArgs&, int, size_t, cudaStream_t);
-int launch_grad3_k0_nt2(const GradArgs&, int, size_t, cudaStream_t);
-int launch_grad3_k0_nt3(const GradArgs&, int, size_t, cudaStream_t);
-int launch_grad3_k0_nt4(const GradArgs&, int, size_t, cudaStream_t);
-int launch_grad3_k1_nt1(const GradArgs&, int, size_t, cudaStream_t);
-int launch_grad3_k1_nt2(const GradArgs&, int, size_t, cudaStream_t);
-int launch_grad3_k1_nt3(const GradArgs&, int, size_t, cudaStream_t);
-int launch_grad3_k1_nt4(const GradArgs&, int, size_t, cudaStream_t);
+int launch_grad3_k0_nt1(const GradArgs&, int, size_t, int, cudaStream_t);
+int launch_grad3_k0_nt2(const GradArgs&, int, size_t, int, cudaStream_t);
+int launch_grad3_k0_nt3(const GradArgs&, int, size_t, int, cudaStream_t);
+int launch_grad3_k0_nt4(const GradArgs&, int, size_t, int, cudaStream_t);
+int launch_grad3_k1_nt1(const GradArgs&, int, size_t, int, cudaStream_t);
+int launch_grad3_k1_nt2(const GradArgs&, int, size_t, int, cudaStream_t);
+int launch_grad3_k1_nt3(const GradArgs&, int, size_t, int, cudaStream_t);
+int launch_grad3_k1_nt4(const GradArgs&, int, size_t, int, cudaStream_t);
 
 static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
   static const int table[][2] = {{4, 16}, {8, 8}, {12, 5}, {16, 4}, {20, 3}, {24, 2}, {32, 2}, {48, 1}, {64, 1}};
@@ -225,6 +226,7 @@ static int plan_grad(int p, int B, int kind, int sms, GradPlan* pl) {
     const size_t sm3 = g3::smem_bytes(NT, B, kind, 16);
     if (sm3 <= 227 * 1024) {
       pl->v3 = 1; pl->NT3 = NT; pl->smem = sm3; pl->gy = 1; pl->threads = 512;
+      if (const char* e = std::getenv("ACE_GRAD3_CW")) pl->cw3 = std::atoi(e) != 0;
       return 0;
     }
   }
@@ -287,18 +289,49 @@ static int launch_grad_t(const GradArgs& a, int kind, const GradPlan& pl, cudaSt
 
 static int launch_grad2(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st);
 
+// per-device ordering of the launches that use grad3's constant-memory table (see launch_grad)
+struct G3Chain {
+  std::mutex mu;
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+};
+static G3Chain& g3_chain(int dev) {
+  static G3Chain chains[64];
+  return chains[dev & 63];
+}
+
 static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
   if (pl.v3) {
-    switch (kind * 10 + pl.NT3) {
-      case 1: return launch_grad3_k0_nt1(a, pl.gx, pl.smem, st);
-      case 2: return launch_grad3_k0_nt2(a, pl.gx, pl.smem, st);
-      case 3: return launch_grad3_k0_nt3(a, pl.gx, pl.smem, st);
-      case 4: return launch_grad3_k0_nt4(a, pl.gx, pl.smem, st);
-      case 11: return launch_grad3_k1_nt1(a, pl.gx, pl.smem, st);
-      case 12: return launch_grad3_k1_nt2(a, pl.gx, pl.smem, st);
-      case 13: return launch_grad3_k1_nt3(a, pl.gx, pl.smem, st);
-      default: return launch_grad3_k1_nt4(a, pl.gx, pl.smem, st);
-    }
+    auto go = [&](int cw) -> int {
+      switch (kind * 10 + pl.NT3) {
+        case 1: return launch_grad3_k0_nt1(a, pl.gx, pl.smem, cw, st);
+        case 2: return launch_grad3_k0_nt2(a, pl.gx, pl.smem, cw, st);
+        case 3: return launch_grad3_k0_nt3(a, pl.gx, pl.smem, cw, st);
+        case 4: return launch_grad3_k0_nt4(a, pl.gx, pl.smem, cw, st);
+        case 11: return launch_grad3_k1_nt1(a, pl.gx, pl.smem, cw, st);
+        case 12: return launch_grad3_k1_nt2(a, pl.gx, pl.smem, cw, st);
+        case 13: return launch_grad3_k1_nt3(a, pl.gx, pl.smem, cw, st);
+        default: return launch_grad3_k1_nt4(a, pl.gx, pl.smem, cw, st);
+      }
+    };
+    if (!pl.cw3) return go(0);
+    // The constant-memory table is one per module: [wait for the previous user's kernel] -> copy -> kernel -> [record],
+    // enqueued under a per-device lock, serialises the gradient launches of different fit handles on one device
+    // (all other work of the handles still overlaps).  Inside a stream capture the wait / record become external
+    // event nodes, so graph replays of different handles are ordered the same way.
+    int dev = 0;
+    ACE_CUDA(cudaGetDevice(&dev));
+    G3Chain& ch = g3_chain(dev);
+    std::lock_guard<std::mutex> lk(ch.mu);
+    if (ch.ev == nullptr) ACE_CUDA(cudaEventCreateWithFlags(&ch.ev, cudaEventDisableTiming));
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    ACE_CUDA(cudaStreamIsCapturing(st, &cs));
+    const bool cap = cs != cudaStreamCaptureStatusNone;
+    if (ch.recorded) ACE_CUDA(cudaStreamWaitEvent(st, ch.ev, cap ? cudaEventWaitExternal : cudaEventWaitDefault));
+    ACE_TRY(go(1));
+    ACE_CUDA(cudaEventRecordWithFlags(ch.ev, st, cap ? cudaEventRecordExternal : cudaEventRecordDefault));
+    ch.recorded = true;
+    return 0;
   }
   if (pl.v2) return launch_grad2(a, kind, pl, st);
   switch (pl.PD) {

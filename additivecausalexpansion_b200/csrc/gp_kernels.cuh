@@ -40,6 +40,16 @@ __global__ void prep_tables_kernel(const double* __restrict__ theta, int p, int 
     if (d < p && c <= B) w = exp(-theta[1 + B + B * d + c]);
     tab[TAB_WE + idx] = w;
   }
+  for (int idx = t; idx < G3_SIZE; idx += blockDim.x) {  // compact block for the constant-memory gradient kernels
+    double w = 0.0;
+    if (idx < G3_LAM) {
+      if (idx < B) w = theta[2 + idx];
+    } else {
+      const int d = (idx - G3_LAM) / G3_WS, c = (idx - G3_LAM) % G3_WS;
+      if (d < p && c <= B) w = exp(-theta[1 + B + B * d + c]);
+    }
+    tab[TAB_G3 + idx] = w;
+  }
 }
 
 __global__ void logabs_kernel(const double* __restrict__ z, double* __restrict__ lz, size_t count) {

@@ -9,12 +9,21 @@
 //     no uniform `b < B` branches are left in the loop body;
 //   * exp / sqrt / reciprocal run in lock step over G terms (fastmath.cuh: fast_*_n), so the schedule has G
 //     independent dependency chains where the scalar calls were issued back to back;
-//   * the gradient's square roots and reciprocals skip the last rounding-cleanup step (<= 2 ulp instead of <= 1).
+//   * the gradient's square roots and reciprocals skip the last rounding-cleanup step (<= 2 ulp instead of <= 1);
+//   * CW = 1: the length-scale weights and lambda_b live in __constant__ memory (copied there from the device table
+//     before the launch) and the distance loop is fully unrolled, so every weight is a c[3][imm] operand of its DFMA
+//     -- the 7 LDS.128 per (pair, dimension) of the shared-memory version (ncu r02: the distance loop took 37 % of the
+//     samples for 28 % of the FP64 work, stalled on short_scoreboard / mio_throttle) disappear.  One table per
+//     module: launches that use it are serialised per device by the caller (ace_b200.cu: G3Chain).  CW = 0 keeps the
+//     table in shared memory (no serialisation needed).
 // Reference semantics: src/kernel_SE_cpp.cpp:161-243 (grad_SE_cpp), src/kernel_Matern_cpp.cpp:340-377,420-467.
 #pragma once
 #include "pair_common.cuh"
 
 namespace ace {
+
+// lambda_b and we[d][c] of the launch in flight (layout: pair_common.cuh G3_*); one copy per translation unit
+static __constant__ double cG3[G3_SIZE];
 
 namespace g3 {
 constexpr int T = 64;      // tile edge
@@ -31,8 +40,9 @@ inline size_t smem_bytes(int NT, int BX, int kind, int nwarps) {
 }  // namespace g3
 
 // BX additive terms (exact), NT = ceil(p / 8) tiles of length-scale dimensions, G terms per lock-step group
-template <int BX, int NT, int KIND, int NWARPS, int G>
+template <int BX, int NT, int KIND, int NWARPS, int G, int CW>
 __global__ void __launch_bounds__(NWARPS * 32, 1) grad3_kernel(const GradArgs a) {
+  static_assert(BX <= G3_LAM && g3::ne(BX, KIND) <= G3_WS && 8 * NT <= G3_PD, "shape exceeds the constant table");
   using namespace g3;
   constexpr int NTHR = NWARPS * 32;
   constexpr int JCOLS = 128 / NWARPS;  // columns of the 64 x 64 tile per warp
@@ -138,7 +148,24 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) grad3_kernel(const GradArgs a)
       double E[NE];
 #pragma unroll
       for (int c = 0; c < NE; ++c) E[c] = 0.0;
-      {
+      if (CW) {
+        const double* xi = Xi + li;
+        const double* xj = Xj + jj;
+        double* ds = Ds + lane;
+#pragma unroll
+        for (int d0 = 0; d0 < PD8; d0 += 4) {
+          if (d0 >= p4) break;  // uniform
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) {
+            const int d = d0 + dd;
+            const double df = xi[d * T] - xj[d * T];
+            const double d2 = df * df;
+            ds[d * LDS_] = d2;
+#pragma unroll
+            for (int c = 0; c < NE; ++c) E[c] = fma(d2, cG3[G3_LAM + d * G3_WS + c], E[c]);
+          }
+        }
+      } else {
         const double* xi = Xi + li;
         const double* xj = Xj + jj;
         double* ds = Ds + lane;
@@ -202,7 +229,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) grad3_kernel(const GradArgs a)
           if (KIND == 0) {
             // sign(z_first) sign(z_second) exp(lambda - D + log|z_first| + log|z_second|), first = column point
             // (the smaller index of a lower-triangle pair; src/kernel_SE_cpp.cpp:103-119)
-            double arg = lam[b] - E[b];
+            double arg = (CW ? cG3[b] : lam[b]) - E[b];
             if (b > 0) arg = arg + LZj[(b - 1) * T + jj] + LZi[(b - 1) * T + li];
             ex[k] = arg;
             live[k] = (b == 0) || !(zj == 0.0 || zi == 0.0);
@@ -210,7 +237,7 @@ __global__ void __launch_bounds__(NWARPS * 32, 1) grad3_kernel(const GradArgs a)
           } else {
             // (1 + sqrt3 r) exp(lambda - sqrt3 r) z_first z_second (src/kernel_Matern_cpp.cpp:217,227)
             const double sr = SQRT3 * E[b];
-            ex[k] = lam[b] - sr;
+            ex[k] = (CW ? cG3[b] : lam[b]) - sr;
             den[k] = 1.0 + sr;
             zz[k] = zj;
             live[k] = true;

@@ -17,7 +17,12 @@ constexpr int TAB_LAM = 8;                        // lambda_b            [BMAXT]
 // GRADIENT differentiates theta[2 + B + b + B*d] = we[d][b+1]: one table, shifted by one column.
 constexpr int WSTRIDE = 36;
 constexpr int TAB_WE = TAB_LAM + BMAXT;
-constexpr int TAB_SIZE = TAB_WE + PMAX * WSTRIDE;
+// Compact copy for the constant-memory gradient kernels (grad3_kernel.cuh): lambda_b [G3_LAM] followed by
+// we[d][c] as [G3_PD][G3_WS] -- one contiguous block, copied into __constant__ memory before the gradient launch.
+constexpr int G3_LAM = 16, G3_PD = 32, G3_WS = 18;
+constexpr int G3_SIZE = G3_LAM + G3_PD * G3_WS;
+constexpr int TAB_G3 = TAB_WE + PMAX * WSTRIDE;
+constexpr int TAB_SIZE = TAB_G3 + G3_SIZE;
 
 __device__ __forceinline__ double sgn(double x) { return (double)((0.0 < x) - (x < 0.0)); }
 

@@ -12,8 +12,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "full":
 for cfg, n in shapes:
     prob = synth.make_problem(cfg, n=n)
     ref = None
-    for impl in (2, 3):
-        os.environ["ACE_GRAD_IMPL"] = str(impl); os.environ["ACE_GRAD2_WARPS"] = "16"
+    for impl, cw in ((2, 0), (3, 0), (3, 1)):
+        os.environ["ACE_GRAD_IMPL"] = str(impl); os.environ["ACE_GRAD2_WARPS"] = "16"; os.environ["ACE_GRAD3_CW"] = str(cw)
         with AceFit(prob.y, prob.X, prob.Z, prob.parameters, kernel=prob.kernel, std_y=prob.std_y, use_graph=False) as f:
             ts = []
             for it in range(1, 5):
@@ -23,6 +23,6 @@ for cfg, n in shapes:
         if ref is None:
             ref = (g, st)
         dg = float(np.abs(g - ref[0]).max() / np.abs(ref[0]).max())
-        out[f"{cfg}_n{n}_impl{impl}"] = {"grad_ms": min(ts), "evidence": st[1], "rmse": st[0], "gnorm": gn, "dgrad_rel_vs_impl2": dg}
-        print(cfg, n, "impl", impl, "grad ms", round(min(ts), 3), "evidence", st[1], "rmse", st[0], "dgrad", dg, flush=True)
+        out[f"{cfg}_n{n}_impl{impl}_cw{cw}"] = {"grad_ms": min(ts), "evidence": st[1], "rmse": st[0], "gnorm": gn, "dgrad_rel_vs_impl2": dg}
+        print(cfg, n, "impl", impl, "cw", cw, "grad ms", round(min(ts), 3), "evidence", st[1], "rmse", st[0], "dgrad", dg, flush=True)
 json.dump(out, open('/root/repo/gpurun_out/r02_grad_sweep3.json', 'w'), indent=1)
