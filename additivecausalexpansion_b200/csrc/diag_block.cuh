@@ -22,6 +22,7 @@
 // shared-memory stage filled by TMA bulk copies (cp.async.bulk, L2 -> smem) on a per-warp mbarrier.  Replaces the eigendecomposition
 // route of invkernel_cpp for the diagonal blocks (src/kernel_SE_cpp.cpp:137-157).
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "fastmath.cuh"
 
@@ -42,13 +43,14 @@ struct DiagArgs {
 
 namespace dg {
 constexpr int TS = 32;                    // tile edge
-constexpr int NC = 8;                     // CTAs per cluster (portable maximum)
+// CTAs per cluster: 8 (portable maximum) or 16 (opt-in, cudaFuncAttributeNonPortableClusterSizeAllowed): template
+// parameter of the kernel.  With 8 the first tile columns of a 512-block are bound by the 56 worker warps (13-15 us of
+// trailing update against a 13 us serial chain, profiles/r02/diag_block_timeline.md); 16 CTAs halve that.
 constexpr int WARPS = 8, THREADS = WARPS * 32;
-constexpr int GW = NC * WARPS;            // warps in the cluster
 constexpr int LDT = 36;                   // stride of a staged tile: rows 16-byte aligned, DMMA fragment loads conflict free
-constexpr int STAGE = 2 * TS * LDT + 2;   // doubles per warp: one A tile + one B tile + (mbarrier, its phase)
-constexpr size_t SMEM_BYTES = (size_t)WARPS * STAGE * 8;
-constexpr uint32_t TILE_PAIR_BYTES = 2 * TS * TS * 8;
+constexpr int STAGE = 2 * TS * LDT + 2;   // doubles per warp: one A tile + one B tile (+ 2 spare)
+constexpr int COLBARS = 32;               // one mbarrier per column of the diagonal tile: leader -> follower hand-over
+constexpr size_t SMEM_BYTES = (size_t)(WARPS * STAGE + COLBARS) * 8;
 constexpr int KEEP_ALL = 0, KEEP_UPPER = 1, KEEP_LOWER = 2;
 inline size_t ws_doubles(int panel_blocks) {
   const size_t N = (size_t)panel_blocks * 128;
@@ -67,22 +69,32 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// Two 32 x 32 tiles (column c at src + c * ld) -> the warp's stage (column c at dst + c * LDT): lane c moves column c
-// of both with one TMA bulk copy each (256 B), completion on the warp's own mbarrier.
+// split form: a warp that has published its part may go on and collect the barrier later
+__device__ __forceinline__ void cluster_arrive() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Two 32 x 32 tiles (column c at src + c * ld) -> the warp's stage (column c at dst + c * LDT) with 16-byte loads
+// through L2 (ld.global.cg): 16 lanes per column, 32 loads per lane in flight, ~0.4 us.  (The first version used one
+// 256-byte TMA bulk copy per lane and tile: 64 serialised UBLKCP issues cost ~3 us per tile pair, more than the tile
+// product itself -- profiles/r02/diag_block_timeline.md.)  Operands must be 16-byte aligned with even strides.
 __device__ __forceinline__ void dg_stage_pair(double* stage, const double* A, long lda, const double* B, long ldb,
                                               int lane) {
   using namespace dg;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * TS * LDT);
-  uint32_t* ph = reinterpret_cast<uint32_t*>(bar + 1);
-  const uint32_t phase = *ph;
-  fence_proxy_async();  // the stage doubles as scratch of the tile factorisation (generic-proxy accesses)
-  if (lane == 0) mbar_arrive_expect_tx(bar, TILE_PAIR_BYTES);
+  const int r2 = 2 * (lane & 15), c0 = lane >> 4;
+  double2 va[16], vb[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) va[q] = __ldcg(reinterpret_cast<const double2*>(A + r2 + (size_t)(2 * q + c0) * lda));
+#pragma unroll
+  for (int q = 0; q < 16; ++q) vb[q] = __ldcg(reinterpret_cast<const double2*>(B + r2 + (size_t)(2 * q + c0) * ldb));
+#pragma unroll
+  for (int q = 0; q < 16; ++q) *reinterpret_cast<double2*>(stage + r2 + (2 * q + c0) * LDT) = va[q];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) *reinterpret_cast<double2*>(stage + TS * LDT + r2 + (2 * q + c0) * LDT) = vb[q];
   __syncwarp();
-  tma_bulk_g2s(stage + lane * LDT, A + (size_t)lane * lda, TS * 8, bar);
-  tma_bulk_g2s(stage + TS * LDT + lane * LDT, B + (size_t)lane * ldb, TS * 8, bar);
-  mbar_wait(bar, phase);
-  __syncwarp();
-  if (lane == 0) *ph = phase ^ 1u;
 }
 
 // One warp:  C = beta * C + alpha * sum_{t < nk} A_t B_t^T  on 32 x 32 tiles (A_t at A + t * sa, B_t at B + t * sb),
@@ -92,31 +104,35 @@ __device__ __forceinline__ void dg_stage_pair(double* stage, const double* A, lo
 __device__ __noinline__ void dg_tile_gemm(double* stage, int lane, const double* A, long lda, long sa, int ma_t,
                                              int ma_kind, const double* B, long ldb, long sb, int mb_t, int mb_kind,
                                              int nk, double alpha, double beta, double* C, long ldc, double* Ct,
-                                             long ldct) {
+                                             long ldct, long long* tdbg = nullptr) {
   using namespace dg;
   const int g = lane >> 2, tq = lane & 3;
   double acc[4][4][2];
-  if (beta != 0.0) {  // acc = (beta / alpha) C, so that alpha * acc ends as beta C + alpha sum
-    const double sc = beta / alpha;
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-          acc[mt][nt][e] = sc * __ldcg(C + (mt * 8 + g) + (size_t)(nt * 8 + 2 * tq + e) * ldc);
-  } else {
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  }
+  if (tdbg != nullptr && lane == 0) tdbg[0] = clock64();
   double* sA = stage;
   double* sB = stage + TS * LDT;
 #pragma unroll 1
   for (int t = 0; t < nk; ++t) {
-    __syncwarp();  // everybody is done reading the previous tiles (and has seen the phase word)
+    __syncwarp();  // everybody is done reading the previous tiles
     dg_stage_pair(stage, A + (size_t)t * sa, lda, B + (size_t)t * sb, ldb, lane);
+    if (t == 0) {
+      if (beta != 0.0) {  // acc = (beta / alpha) C, so that alpha * acc ends as beta C + alpha sum
+        const double sc = beta / alpha;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              acc[mt][nt][e] = sc * __ldcg(C + (mt * 8 + g) + (size_t)(nt * 8 + 2 * tq + e) * ldc);
+      } else {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+      }
+    }
+    if (tdbg != nullptr && lane == 0) tdbg[1] = clock64();
     const int ka = (t == ma_t) ? ma_kind : KEEP_ALL, kb = (t == mb_t) ? mb_kind : KEEP_ALL;
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
@@ -144,6 +160,7 @@ __device__ __noinline__ void dg_tile_gemm(double* stage, int lane, const double*
         for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
   }
+  if (tdbg != nullptr && lane == 0) tdbg[2] = clock64();
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -154,6 +171,7 @@ __device__ __noinline__ void dg_tile_gemm(double* stage, int lane, const double*
         acc[mt][nt][e] = v;
         __stcg(C + (mt * 8 + g) + (size_t)(nt * 8 + 2 * tq + e) * ldc, v);
       }
+  if (tdbg != nullptr && lane == 0) tdbg[3] = clock64();
   if (Ct != nullptr) {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
@@ -173,7 +191,7 @@ __device__ __noinline__ void dg_tile_gemm(double* stage, int lane, const double*
 // ---------------------------------------------------------------------------------------------
 template <int JB, int H>
 __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, double* colbuf, double* dg_, double* idg,
-                                             int tx, int ty, int* info, int gidx0, volatile int* progress, int base) {
+                                             int tx, int ty, int* info, int gidx0, uint64_t* colbar) {
   constexpr int A0 = 2 * JB + H;  // row block of the pivots of these 4 columns
 #pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
@@ -184,31 +202,37 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, doub
       for (int a = A0; a < 8; ++a) cb[4 * a + ty] = r[a][JB];
     }
     __syncwarp();
-    if (tx == 0 && ty == 0 && j > 0) {  // columns < j of L and their 1/L_jj are in shared memory: the follower may go on
-      __threadfence_block();
-      *progress = base + j;
-    }
+    // column j-1 of L and 1/L_(j-1)(j-1) are in shared memory (stored at the end of the previous iteration, ordered
+    // by the __syncwarp above): hand them to the follower.  mbarrier.arrive has release semantics at CTA scope and
+    // costs one instruction (the MEMBAR.SC.CTA of a fence + flag store was ~3 us per tile on the critical path).
+    if (tx == 0 && ty == 0 && j > 0) mbar_arrive(colbar + j - 1);
     const double pj = cb[j];
-    // one MUFU-seeded reciprocal square root serves the whole column: 1/L_jj = y, L_jj = p y, 1/p = y^2
-    const double inv = fast_rsqrt(pj);
-    const double invp = inv * inv;
+    // one MUFU-seeded reciprocal square root serves the whole column: 1/L_jj = y, L_jj = p y, 1/p = y^2.  One cubic
+    // step on the ~2^-23 seed leaves ~2^-60: the second step of fast_rsqrt is off this chain.
+    double inv;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(pj));
+    {
+      const double e = fma(-pj * inv, inv, 1.0);
+      inv = fma(inv * e, fma(0.375, e, 0.5), inv);
+    }
     double lm[8], cm[4];
 #pragma unroll
-    for (int a = A0; a < 8; ++a) lm[a] = cb[4 * a + ty] * invp;
+    for (int a = A0; a < 8; ++a) lm[a] = cb[4 * a + ty] * inv;
 #pragma unroll
-    for (int b = JB; b < 4; ++b) cm[b] = cb[8 * b + tx];
+    for (int b = JB; b < 4; ++b) cm[b] = cb[8 * b + tx] * inv;
     lm[A0] = (ty > jj) ? lm[A0] : 0.0;   // rows <= j (only block A0 straddles the pivot)
     cm[JB] = (tx > jx) ? cm[JB] : 0.0;   // columns <= j (only block JB straddles it)
+    // the block column that holds the next pivot column first
 #pragma unroll
-    for (int a = A0; a < 8; ++a)
+    for (int b = JB; b < 4; ++b)
 #pragma unroll
-      for (int b = JB; b < 4; ++b) r[a][b] = fma(-lm[a], cm[b], r[a][b]);  // entries above the diagonal: never read
+      for (int a = A0; a < 8; ++a) r[a][b] = fma(-lm[a], cm[b], r[a][b]);  // entries above the diagonal: never read
     // the column of L leaves AFTER the update was issued: it is off the critical path (the owners' copy of column j
     // is untouched by the update: their cm[JB] is masked to zero)
     if (tx == jx) {
-      if (ty > jj) Ls[4 * A0 + ty + j * 33] = r[A0][JB] * inv;  // the pivot's row block: rows below the pivot only
+      if (ty > jj) Ls[4 * A0 + ty + j * 33] = lm[A0];  // the pivot's row block: rows below the pivot only
 #pragma unroll
-      for (int a = A0 + 1; a < 8; ++a) Ls[4 * a + ty + j * 33] = r[a][JB] * inv;
+      for (int a = A0 + 1; a < 8; ++a) Ls[4 * a + ty + j * 33] = lm[a];
       if (ty == jj) {  // the pivot itself (one lane): L_jj by one Newton step on p y, 1 / L_jj, positivity check
         double sq = pj * inv;
         sq = fma(fma(-sq, sq, pj), 0.5 * inv, sq);
@@ -224,15 +248,13 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, doub
 // r(i, :) -= L(i, j) X(j, :) for i > j.  X(j, k), k < j goes to the upper triangle of Ls as U(k, j).
 template <int A>
 __device__ __forceinline__ void dg_inv_rows(double (&r)[8][4], double* Ls, double* rowbuf, const double* idg, int tx,
-                                            int ty, const volatile int* progress, int base) {
+                                            int ty, uint64_t* colbar, uint32_t parity) {
   constexpr int BMAX = A / 2;  // column blocks 0 .. BMAX hold the columns k <= j
 #pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
     const int j = 4 * A + jj;
     double* rb = rowbuf + (j & 1) * 32;
-    while (*progress < base + j + 1) {  // column j of L published by the factoring warp?
-    }
-    __threadfence_block();
+    mbar_wait(colbar + j, parity);  // column j of L published by the factoring warp (acquire)
     if (ty == jj) {
       const double dj = idg[j];
 #pragma unroll
@@ -263,9 +285,11 @@ __device__ __forceinline__ void dg_inv_rows(double (&r)[8][4], double* Ls, doubl
 // The diagonal tile is factored by TWO warps of one CTA: the leader runs the Cholesky (and writes L, diag(L)), the
 // follower computes X = L^-1 one column behind it -- row j of X only needs columns <= j of L -- and writes the X / U
 // tile.  Both work on the leader's shared-memory stage `sm0` (columns of L below the diagonal, rows of U above it);
-// `progress` counts the columns the leader has published, monotonically over the tiles this CTA factors.
-__device__ __noinline__ void dg_chol_lead(double* sm0, int lane, double* At, long ld, double* dv, int* info, int gidx0,
-                                          volatile int* progress, int base) {
+// column j is handed over on the mbarrier colbar[j] (phase parity = how often this CTA has factored a tile, mod 2).
+// SRC_SMEM: the tile is taken from shared memory (`tile`, element (i, c) at tile[i + 33 c]) instead of from At.
+template <bool SRC_SMEM>
+__device__ __noinline__ void dg_chol_lead(double* sm0, int lane, double* At, long ld, const double* tile, double* dv,
+                                          int* info, int gidx0, uint64_t* colbar) {
   double* Ls = sm0;                 // [32][33]: strictly lower = L, strictly upper = U (filled by the follower)
   double* colbuf = sm0 + 32 * 33;   // 2 x 32: pivot column, double buffered
   double* dgl = colbuf + 64;        // L_jj
@@ -275,20 +299,19 @@ __device__ __noinline__ void dg_chol_lead(double* sm0, int lane, double* At, lon
 #pragma unroll
   for (int b = 0; b < 4; ++b)
 #pragma unroll
-    for (int a = 0; a < 8; ++a) r[a][b] = __ldcg(At + (4 * a + ty) + (size_t)(8 * b + tx) * ld);
-  dg_chol_cols<0, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
-  dg_chol_cols<0, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
-  dg_chol_cols<1, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
-  dg_chol_cols<1, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
-  dg_chol_cols<2, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
-  dg_chol_cols<2, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
-  dg_chol_cols<3, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
-  dg_chol_cols<3, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, progress, base);
+    for (int a = 0; a < 8; ++a)
+      r[a][b] = SRC_SMEM ? tile[(4 * a + ty) + (8 * b + tx) * 33] : __ldcg(At + (4 * a + ty) + (size_t)(8 * b + tx) * ld);
+  __syncwarp();  // SRC_SMEM: `tile` overlaps idg, which the first column writes
+  dg_chol_cols<0, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  dg_chol_cols<0, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  dg_chol_cols<1, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  dg_chol_cols<1, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  dg_chol_cols<2, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  dg_chol_cols<2, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  dg_chol_cols<3, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  dg_chol_cols<3, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
   __syncwarp();
-  if (lane == 0) {
-    __threadfence_block();
-    *progress = base + 32;
-  }
+  if (lane == 0) mbar_arrive(colbar + 31);
   // L out: column c, lane = row (coalesced)
 #pragma unroll 4
   for (int c = 0; c < 32; ++c) {
@@ -300,7 +323,7 @@ __device__ __noinline__ void dg_chol_lead(double* sm0, int lane, double* At, lon
 }
 
 __device__ __noinline__ void dg_inv_follow(double* sm0, double* sm_own, int lane, double* St, long lds,
-                                           const volatile int* progress, int base) {
+                                           uint64_t* colbar, uint32_t parity) {
   double* Ls = sm0;
   const double* idg = sm0 + 32 * 33 + 96;
   double* rowbuf = sm_own;  // 2 x 32 in the follower's own stage
@@ -310,14 +333,14 @@ __device__ __noinline__ void dg_inv_follow(double* sm0, double* sm_own, int lane
   for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) r[a][b] = (4 * a + ty == 8 * b + tx) ? 1.0 : 0.0;
-  dg_inv_rows<0>(r, Ls, rowbuf, idg, tx, ty, progress, base);
-  dg_inv_rows<1>(r, Ls, rowbuf, idg, tx, ty, progress, base);
-  dg_inv_rows<2>(r, Ls, rowbuf, idg, tx, ty, progress, base);
-  dg_inv_rows<3>(r, Ls, rowbuf, idg, tx, ty, progress, base);
-  dg_inv_rows<4>(r, Ls, rowbuf, idg, tx, ty, progress, base);
-  dg_inv_rows<5>(r, Ls, rowbuf, idg, tx, ty, progress, base);
-  dg_inv_rows<6>(r, Ls, rowbuf, idg, tx, ty, progress, base);
-  dg_inv_rows<7>(r, Ls, rowbuf, idg, tx, ty, progress, base);
+  dg_inv_rows<0>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
+  dg_inv_rows<1>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
+  dg_inv_rows<2>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
+  dg_inv_rows<3>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
+  dg_inv_rows<4>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
+  dg_inv_rows<5>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
+  dg_inv_rows<6>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
+  dg_inv_rows<7>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
   __syncwarp();
   // X (lower) / U (upper) tile out: column c, lane = row.  X(i, c) = U(c, i) = Ls[c + i * 33] for i > c.
 #pragma unroll 4
@@ -328,8 +351,96 @@ __device__ __noinline__ void dg_inv_follow(double* sm0, double* sm_own, int lane
   __syncwarp();
 }
 
-__global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2) diag_block_kernel(const DiagArgs a) {
+// The serial chain of one tile column, run by the warp that will factor tile k+1 (warp 0 of its CTA) right after the
+// barrier that publishes L_kk / X_kk -- it does not wait for the rest of the column solve:
+//   L_(k+1)k = A_(k+1)k X_kk^T        (stored for everybody else; arrives at the second barrier of the step)
+//   A_(k+1)(k+1) -= L_(k+1)k L_(k+1)k^T   (operand straight from the stage, result handed over in shared memory)
+//   Cholesky of the updated tile          (dg_chol_lead, follower one column behind)
+// and only then collects the second barrier.  Round 2's first version ran update + factorisation after that barrier
+// and went through global memory twice: 21.5 us per tile column, of which 10 us were barrier + solve + update.
+__device__ __noinline__ void dg_chain_step(double* stage0, int lane, double* Lk1k, const double* Xkk, long ldx,
+                                           double* Adiag, long ld, double* dv, int* info, int gidx0, uint64_t* colbar,
+                                           long long* dbg) {
   using namespace dg;
+  const int g = lane >> 2, tq = lane & 3;
+  double* sA = stage0;
+  double* sB = stage0 + TS * LDT;
+  dg_stage_pair(stage0, Lk1k, ld, Xkk, ldx, lane);
+  double acc[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const int k = ks * 4 + tq;
+    double a[4], b[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) a[mt] = sA[mt * 8 + g + k * LDT];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int row = nt * 8 + g;
+      const double v = sB[row + k * LDT];
+      b[nt] = (row >= k) ? v : 0.0;  // X_kk is lower triangular; its upper part holds U
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+  __syncwarp();  // everybody is done reading the staged operands
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int row = mt * 8 + g, col = nt * 8 + 2 * tq + e;
+        __stcg(Lk1k + row + (size_t)col * ld, acc[mt][nt][e]);
+        sA[row + col * LDT] = acc[mt][nt][e];
+      }
+  cluster_arrive();  // second barrier of the step: L_(k+1)k is published; collected after the factorisation
+  // the diagonal tile (all updates of earlier columns were complete at the first barrier); the accumulators of the
+  // first product are dead by now (two live 32 x 32 fragment sets would not fit 128 registers)
+  double c[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) c[mt][nt][e] = __ldcg(Adiag + (mt * 8 + g) + (size_t)(nt * 8 + 2 * tq + e) * ld);
+  __syncwarp();
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const int k = ks * 4 + tq;
+    double a[4], b[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) a[mt] = -sA[mt * 8 + g + k * LDT];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = sA[nt * 8 + g + k * LDT];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
+  }
+  // hand the updated tile to the factorisation's register layout through the B half of the stage (stride 33)
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) sB[(mt * 8 + g) + (nt * 8 + 2 * tq + e) * 33] = c[mt][nt][e];
+  __syncwarp();
+  if (dbg != nullptr && lane == 0) dbg[1] = clock64();
+  dg_chol_lead<true>(stage0, lane, Adiag, ld, sB, dv, info, gidx0, colbar);
+  if (dbg != nullptr && lane == 0) dbg[2] = clock64();
+  cluster_wait();
+}
+
+template <int NC>
+__global__ void __launch_bounds__(dg::THREADS, 2) diag_block_kernel(const DiagArgs a) {
+  using namespace dg;
+  constexpr int GW = NC * WARPS;  // warps in the cluster
   extern __shared__ __align__(128) unsigned char smraw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = (int)cluster_ctarank();
@@ -337,16 +448,13 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
   // bound by the SM's FP64 tensor rate: eight of them on one SM take four times as long as two)
   const int gw = warp * NC + crank;
   double* stage = reinterpret_cast<double*>(smraw) + warp * STAGE;
-  if (lane == 0) {
-    uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * TS * LDT);
-    mbar_init(bar, 1);
-    reinterpret_cast<uint32_t*>(bar + 1)[0] = 0u;  // phase of the warp's mbarrier
-    reinterpret_cast<uint32_t*>(bar + 1)[1] = 0u;  // warp 0 only: columns of L published to the follower (see below)
+  uint64_t* colbar = reinterpret_cast<uint64_t*>(reinterpret_cast<double*>(smraw) + WARPS * STAGE);
+  if (warp == 0) {
+    mbar_init(colbar + lane, 1);  // column hand-over barriers of the tile factorisation
     fence_mbar_init();
   }
   __syncthreads();
   double* stage0 = reinterpret_cast<double*>(smraw);  // warp 0's stage: the tile factorisation lives there
-  volatile int* progress = reinterpret_cast<volatile int*>(stage0 + 2 * TS * LDT + 1) + 1;
   const int nt = a.nblk * 4;            // 32-tiles per side
   const long N = (long)nt * TS;
   const long ld = a.ld;
@@ -380,22 +488,41 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
   // tile k is factored by warp 0 (Cholesky) and warp 1 (inverse, one column behind) of CTA k mod NC
   if (gw == fw(0)) {
     stampF(0, 1);
-    dg_chol_lead(stage0, lane, At(0, 0), ld, dv, a.info, a.blk0 * 128, progress, 0);
+    dg_chol_lead<false>(stage0, lane, At(0, 0), ld, nullptr, dv, a.info, a.blk0 * 128, colbar);
     stampF(0, 2);
   } else if (gw == fw(0) + NC) {
-    dg_inv_follow(stage0, stage, lane, St(0, 0), N, progress, 0);
+    dg_inv_follow(stage0, stage, lane, St(0, 0), N, colbar, 0u);
   }
 #pragma unroll 1
   for (int k = 0; k < nt; ++k) {
     stampT(k, 0);
     cluster_barrier();  // L_kk, X_kk visible; trailing update and accumulations of step k-1 complete
     stampT(k, 1);
-    // column k of L: L_ik = A_ik X_kk^T (in place), and row k of X: X(k, j) = -X_kk AccT(j, k)^T, U(j, k) = X(k, j)^T
+    const bool more = (k + 1 < nt);
+    const int f = fw(k + 1);  // CTA rank of the warps that factor tile k+1 (warp 0: Cholesky, warp 1: inverse)
+    if (more && gw == f) {
+      // the serial chain: solve L_(k+1)k, update and factor tile k+1 (arrives at the second barrier on the way)
+      stampF(k + 1, 0);
+      dg_chain_step(stage0, lane, At(k + 1, k), St(k, k), N, At(k + 1, k + 1), ld, dv + (k + 1) * TS, a.info,
+                    a.blk0 * 128 + (k + 1) * TS, colbar, a.dbg ? a.dbg + 8 * (k + 1) + 5 : nullptr);
+      continue;
+    }
+    if (more && gw == f + NC) {
+      cluster_arrive();
+      dg_inv_follow(stage0, stage, lane, St(k + 1, k + 1), N, colbar, (uint32_t)(((k + 1) / NC) & 1));
+      cluster_wait();
+      continue;
+    }
+    // column k of L: L_ik = A_ik X_kk^T (in place), i > k+1, and row k of X: X(k, j) = -X_kk AccT(j, k)^T,
+    // U(j, k) = X(k, j)^T -- dealt over the warps that are not on the chain
     {
-      const int nsolve = nt - 1 - k;
-      for (int u = gw; u < nsolve + k; u += GW) {
+      const int skip = more ? 1 : 0;               // tile (k+1, k) belongs to the chain
+      const int nsolve = nt - 1 - k - skip;
+      const int nw = more ? GW - 2 : GW;
+      const int me = more ? gw - (gw > f) - (gw > f + NC) : gw;
+      for (int u = me; u < nsolve + k; u += nw) {
         if (u < nsolve) {
-          const int i = k + 1 + u;
+          const int i = k + 1 + skip + u;
           dg_tile_gemm(stage, lane, At(i, k), ld, 0, -1, KEEP_ALL, St(k, k), N, 0, 0, KEEP_LOWER, 1, 1.0, 0.0, At(i, k), ld,
                        nullptr, 0);
         } else {
@@ -408,24 +535,12 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
     stampT(k, 2);
     cluster_barrier();  // column k of L and row k of X / column k of U visible
     stampT(k, 3);
-    if (k + 1 >= nt) break;
-    // The warp that factors tile k+1 updates it and goes on factoring (look-ahead).  The warps of the OTHER CTAs share
+    if (!more) break;
+    // The warps of the CTAs that do not hold the chain share
     //   trailing update  A_ij -= L_ik L_jk^T           for k < j <= i        (column-major order, without (k+1, k+1))
     //   accumulation     AccT(j, i) (+)= U(j, k) L_ik^T  for j <= k < i
-    // (the factoring warp's CTA stays out of it: its SM's FP64 pipe belongs to the serial chain).
-    const int f = fw(k + 1);  // also the CTA rank of the factoring warp
-    if (gw == f) {
-      stampF(k + 1, 0);
-      dg_tile_gemm(stage, lane, At(k + 1, k), ld, 0, -1, KEEP_ALL, At(k + 1, k), ld, 0, -1, KEEP_ALL, 1, -1.0, 1.0,
-                   At(k + 1, k + 1), ld, nullptr, 0);
-      __syncwarp();
-      stampF(k + 1, 1);
-      dg_chol_lead(stage0, lane, At(k + 1, k + 1), ld, dv + (k + 1) * TS, a.info, a.blk0 * 128 + (k + 1) * TS, progress,
-                   32 * ((k + 1) / NC));
-      stampF(k + 1, 2);
-    } else if (gw == f + NC) {  // warp 1 of the factoring CTA
-      dg_inv_follow(stage0, stage, lane, St(k + 1, k + 1), N, progress, 32 * ((k + 1) / NC));
-    } else if (crank != f) {
+    // (the factoring CTA stays out of it: its SM's FP64 pipe belongs to the serial chain).
+    if (crank != f) {
       constexpr int NWK = (NC - 1) * WARPS;                        // worker warps
       const int me = warp * (NC - 1) + (crank - f - 1 + NC) % NC;  // 0 .. NWK-1, CTA index fastest
       const int m = nt - 1 - k;                                    // trailing tile rows / columns
@@ -441,7 +556,7 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
           }
           const int i = k + 1 + jj + rest, j = k + 1 + jj;
           dg_tile_gemm(stage, lane, At(i, k), ld, 0, -1, KEEP_ALL, At(j, k), ld, 0, -1, KEEP_ALL, 1, -1.0, 1.0, At(i, j), ld,
-                       nullptr, 0);
+                       nullptr, 0, (a.dbg != nullptr && u == 0) ? a.dbg + 8 * (20 + k) : nullptr);
         } else {
           const int v = u - nupd, i = k + 1 + v % m, j = v / m;
           dg_tile_gemm(stage, lane, St(j, k), N, 0, (j == k) ? 0 : -1, KEEP_UPPER, At(i, k), ld, 0, -1, KEEP_ALL, 1, 1.0,
@@ -479,15 +594,61 @@ __global__ void __cluster_dims__(dg::NC, 1, 1) __launch_bounds__(dg::THREADS, 2)
   stampT(nt, 4 * lvl);
 }
 
+// cluster size in use on this device: 16 when the opt-in size is accepted and can be co-scheduled, else 8
+inline int& diag_cluster_size() {
+  static int nc = 0;
+  return nc;
+}
+
+template <int NC>
+inline int launch_diag_block_nc(const DiagArgs& a, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NC, 1, 1);
+  cfg.blockDim = dim3(dg::THREADS, 1, 1);
+  cfg.dynamicSmemBytes = dg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = NC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  ACE_CUDA(cudaLaunchKernelEx(&cfg, diag_block_kernel<NC>, a));
+  return 0;
+}
+
 inline int configure_diag_kernel() {
-  ACE_CUDA(cudaFuncSetAttribute(diag_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg::SMEM_BYTES));
+  ACE_CUDA(cudaFuncSetAttribute(diag_block_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg::SMEM_BYTES));
+  int want = 16;
+  if (const char* e = std::getenv("ACE_DIAG_CLUSTER")) want = (std::atoi(e) == 8) ? 8 : 16;
+  int nc = 8;
+  if (want == 16 &&
+      cudaFuncSetAttribute(diag_block_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dg::SMEM_BYTES) ==
+          cudaSuccess &&
+      cudaFuncSetAttribute(diag_block_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(16, 1, 1);
+    cfg.blockDim = dim3(dg::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = dg::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 16;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, diag_block_kernel<16>, &cfg) == cudaSuccess && ncl >= 1) nc = 16;
+  }
+  (void)cudaGetLastError();  // a refused opt-in is not an error: the portable size is used
+  diag_cluster_size() = nc;
   return 0;
 }
 
 inline int launch_diag_block(const DiagArgs& a, cudaStream_t st) {
-  diag_block_kernel<<<dg::NC, dg::THREADS, dg::SMEM_BYTES, st>>>(a);
-  ACE_CUDA(cudaGetLastError());
-  return 0;
+  if (diag_cluster_size() == 0) ACE_TRY(configure_diag_kernel());
+  return diag_cluster_size() == 16 ? launch_diag_block_nc<16>(a, st) : launch_diag_block_nc<8>(a, st);
 }
 
 }  // namespace ace

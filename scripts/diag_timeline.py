@@ -38,3 +38,9 @@ for i, v in enumerate(flat):
     print(f"  stamp {i}: +{(v - prev) / GHZ / 1e3:7.2f} us   at {(v - t0) / GHZ / 1e3:8.2f}")
     prev = v
 
+
+print("first trailing-update task of each step (one warp): start -> staged | products | stores (us)")
+for k in range(nt - 1):
+    r = t[20 + k]
+    if r[0]:
+        print(f"{k:2d}: {(r[1]-r[0])/GHZ/1e3:6.2f} {(r[2]-r[1])/GHZ/1e3:6.2f} {(r[3]-r[2])/GHZ/1e3:6.2f}")
