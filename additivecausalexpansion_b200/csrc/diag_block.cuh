@@ -189,26 +189,33 @@ __device__ __noinline__ void dg_tile_gemm(double* stage, int lane, const double*
 // loops are ROLLED (4 columns per template instance), the code stays a few KB (a fully unrolled row-per-lane
 // version was instruction-fetch bound: 12 us per tile), and all 32 lanes share the rank-1 updates.
 // ---------------------------------------------------------------------------------------------
+// Running pointers of the column loop (kept explicitly: recomputed per column they were a third of the loop body).
+struct DgCholState {
+  double* cbc;     // half of the column buffer that holds the published column j
+  double* cbn;     // the other half: column j+1 is published there
+  double* lsw;     // Ls + ty + 33 j: this lane's rows of column j of L
+  double* dgj;     // dgl + j (L_jj); 1 / L_jj at dgj + 32
+  uint64_t* bar;   // colbar + j - 1
+  int j;
+};
+
+// Columns 8 JB + 4 H .. + 3.  Software-pipelined: column j+1 is published to the column buffer as soon as its block
+// column has received the update of column j; the rest of the update and the stores of column j then overlap the
+// STS -> __syncwarp -> LDS round trip of the hand-over.
 template <int JB, int H>
-__device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, double* colbuf, double* dg_, double* idg,
-                                             int tx, int ty, int* info, int gidx0, uint64_t* colbar) {
+__device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], DgCholState& st, int tx, int ty, int* info, int gidx0) {
   constexpr int A0 = 2 * JB + H;  // row block of the pivots of these 4 columns
 #pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
-    const int jx = 4 * H + jj, j = 8 * JB + jx;
-    double* cb = colbuf + (j & 1) * 32;
-    if (tx == jx) {
-#pragma unroll
-      for (int a = A0; a < 8; ++a) cb[4 * a + ty] = r[a][JB];
-    }
-    __syncwarp();
-    // column j-1 of L and 1/L_(j-1)(j-1) are in shared memory (stored at the end of the previous iteration, ordered
-    // by the __syncwarp above): hand them to the follower.  mbarrier.arrive has release semantics at CTA scope and
-    // costs one instruction (the MEMBAR.SC.CTA of a fence + flag store was ~3 us per tile on the critical path).
-    if (tx == 0 && ty == 0 && j > 0) mbar_arrive(colbar + j - 1);
-    const double pj = cb[j];
-    // one MUFU-seeded reciprocal square root serves the whole column: 1/L_jj = y, L_jj = p y, 1/p = y^2.  One cubic
-    // step on the ~2^-23 seed leaves ~2^-60: the second step of fast_rsqrt is off this chain.
+    const int jx = 4 * H + jj;
+    __syncwarp();  // column j is in st.cbc (published at the end of the previous iteration / before the first)
+    // column j-1 of L and 1/L_(j-1)(j-1) are in shared memory (stored in the previous iteration, ordered by the
+    // __syncwarp above): hand them to the follower.  mbarrier.arrive has release semantics at CTA scope and costs one
+    // instruction (the MEMBAR.SC.CTA of a fence + flag store was ~3 us per tile on the critical path).
+    if (tx == 0 && ty == 0 && st.j > 0) mbar_arrive(st.bar);
+    const double pj = st.cbc[st.j];
+    // one MUFU-seeded reciprocal square root serves the whole column: 1/L_jj = y, L_jj = p y.  One cubic step on the
+    // ~2^-23 seed leaves ~2^-60: the second step of fast_rsqrt is off this chain.
     double inv;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(pj));
     {
@@ -216,69 +223,61 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], double* Ls, doub
       inv = fma(inv * e, fma(0.375, e, 0.5), inv);
     }
     double lm[8], cm[4];
+    const double* cl = st.cbc + ty;
+    const double* cc = st.cbc + tx;
 #pragma unroll
-    for (int a = A0; a < 8; ++a) lm[a] = cb[4 * a + ty] * inv;
+    for (int a = A0; a < 8; ++a) lm[a] = cl[4 * a] * inv;
 #pragma unroll
-    for (int b = JB; b < 4; ++b) cm[b] = cb[8 * b + tx] * inv;
+    for (int b = JB; b < 4; ++b) cm[b] = cc[8 * b] * inv;
     lm[A0] = (ty > jj) ? lm[A0] : 0.0;   // rows <= j (only block A0 straddles the pivot)
     cm[JB] = (tx > jx) ? cm[JB] : 0.0;   // columns <= j (only block JB straddles it)
-    // the block column that holds the next pivot column first
+    double* cn = st.cbn + ty;
+    // the block column that holds the next pivot column first (entries above the diagonal: never read)
 #pragma unroll
-    for (int b = JB; b < 4; ++b)
+    for (int a = A0; a < 8; ++a) r[a][JB] = fma(-lm[a], cm[JB], r[a][JB]);
+    if (H == 0 || jj < 3) {
+      if (tx == jx + 1) {
 #pragma unroll
-      for (int a = A0; a < 8; ++a) r[a][b] = fma(-lm[a], cm[b], r[a][b]);  // entries above the diagonal: never read
-    // the column of L leaves AFTER the update was issued: it is off the critical path (the owners' copy of column j
-    // is untouched by the update: their cm[JB] is masked to zero)
+        for (int a = A0; a < 8; ++a) cn[4 * a] = r[a][JB];
+      }
+#pragma unroll
+      for (int b = JB + 1; b < 4; ++b)
+#pragma unroll
+        for (int a = A0; a < 8; ++a) r[a][b] = fma(-lm[a], cm[b], r[a][b]);
+    } else if (JB < 3) {  // the next column opens block column JB + 1
+      constexpr int JN = (JB < 3) ? JB + 1 : 3;
+#pragma unroll
+      for (int a = A0; a < 8; ++a) r[a][JN] = fma(-lm[a], cm[JN], r[a][JN]);
+      if (tx == 0) {
+#pragma unroll
+        for (int a = A0; a < 8; ++a) cn[4 * a] = r[a][JN];
+      }
+#pragma unroll
+      for (int b = JN + 1; b < 4; ++b)
+#pragma unroll
+        for (int a = A0; a < 8; ++a) r[a][b] = fma(-lm[a], cm[b], r[a][b]);
+    }
+    // column j of L (the owners' copy of column j is untouched by the update: their cm[JB] is masked to zero) goes to
+    // shared memory for the follower, which also writes it out
     if (tx == jx) {
-      if (ty > jj) Ls[4 * A0 + ty + j * 33] = lm[A0];  // the pivot's row block: rows below the pivot only
+      if (ty > jj) st.lsw[4 * A0] = lm[A0];  // the pivot's row block: rows below the pivot only
 #pragma unroll
-      for (int a = A0 + 1; a < 8; ++a) Ls[4 * a + ty + j * 33] = lm[a];
+      for (int a = A0 + 1; a < 8; ++a) st.lsw[4 * a] = lm[a];
       if (ty == jj) {  // the pivot itself (one lane): L_jj by one Newton step on p y, 1 / L_jj, positivity check
         double sq = pj * inv;
         sq = fma(fma(-sq, sq, pj), 0.5 * inv, sq);
-        dg_[j] = sq;
-        idg[j] = inv;
-        if (!(pj > 0.0)) atomicCAS(info, 0, gidx0 + j + 1);
+        st.dgj[0] = sq;
+        st.dgj[32] = inv;
+        if (!(pj > 0.0)) atomicCAS(info, 0, gidx0 + st.j + 1);
       }
     }
-  }
-}
-
-// rows j = 4 A .. 4 A + 3 of X = L^-1 (right-looking substitution on r = I): X(j, :) = r(j, :) / L_jj, then
-// r(i, :) -= L(i, j) X(j, :) for i > j.  X(j, k), k < j goes to the upper triangle of Ls as U(k, j).
-template <int A>
-__device__ __forceinline__ void dg_inv_rows(double (&r)[8][4], double* Ls, double* rowbuf, const double* idg, int tx,
-                                            int ty, uint64_t* colbar, uint32_t parity) {
-  constexpr int BMAX = A / 2;  // column blocks 0 .. BMAX hold the columns k <= j
-#pragma unroll 1
-  for (int jj = 0; jj < 4; ++jj) {
-    const int j = 4 * A + jj;
-    double* rb = rowbuf + (j & 1) * 32;
-    mbar_wait(colbar + j, parity);  // column j of L published by the factoring warp (acquire)
-    if (ty == jj) {
-      const double dj = idg[j];
-#pragma unroll
-      for (int b = 0; b <= BMAX; ++b) {
-        const int k = 8 * b + tx;
-        if (k <= j) {
-          const double x = r[A][b] * dj;
-          rb[k] = x;
-          if (k < j) Ls[k + j * 33] = x;
-        }
-      }
-    }
-    __syncwarp();
-    double lm[8], xm[4];
-#pragma unroll
-    for (int a = A; a < 8; ++a) lm[a] = Ls[4 * a + ty + j * 33];
-    lm[A] = (ty > jj) ? lm[A] : 0.0;
-#pragma unroll
-    for (int b = 0; b <= BMAX; ++b) xm[b] = rb[8 * b + tx];
-    xm[BMAX] = (tx <= 4 * (A % 2) + jj) ? xm[BMAX] : 0.0;  // columns > j of the straddling block
-#pragma unroll
-    for (int a = A; a < 8; ++a)
-#pragma unroll
-      for (int b = 0; b <= BMAX; ++b) r[a][b] = fma(-lm[a], xm[b], r[a][b]);
+    double* t = st.cbc;
+    st.cbc = st.cbn;
+    st.cbn = t;
+    st.lsw += 33;
+    st.dgj += 1;
+    st.bar = st.bar + 1;
+    st.j += 1;
   }
 }
 
@@ -302,138 +301,155 @@ __device__ __noinline__ void dg_chol_lead(double* sm0, int lane, double* At, lon
     for (int a = 0; a < 8; ++a)
       r[a][b] = SRC_SMEM ? tile[(4 * a + ty) + (8 * b + tx) * 33] : __ldcg(At + (4 * a + ty) + (size_t)(8 * b + tx) * ld);
   __syncwarp();  // SRC_SMEM: `tile` overlaps idg, which the first column writes
-  dg_chol_cols<0, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
-  dg_chol_cols<0, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
-  dg_chol_cols<1, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
-  dg_chol_cols<1, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
-  dg_chol_cols<2, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
-  dg_chol_cols<2, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
-  dg_chol_cols<3, 0>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
-  dg_chol_cols<3, 1>(r, Ls, colbuf, dgl, idg, tx, ty, info, gidx0, colbar);
+  DgCholState st;
+  st.cbc = colbuf;
+  st.cbn = colbuf + 32;
+  st.lsw = Ls + ty;
+  st.dgj = dgl;
+  st.bar = colbar - 1;
+  st.j = 0;
+  if (tx == 0) {  // publish column 0
+#pragma unroll
+    for (int a = 0; a < 8; ++a) st.cbc[4 * a + ty] = r[a][0];
+  }
+  dg_chol_cols<0, 0>(r, st, tx, ty, info, gidx0);
+  dg_chol_cols<0, 1>(r, st, tx, ty, info, gidx0);
+  dg_chol_cols<1, 0>(r, st, tx, ty, info, gidx0);
+  dg_chol_cols<1, 1>(r, st, tx, ty, info, gidx0);
+  dg_chol_cols<2, 0>(r, st, tx, ty, info, gidx0);
+  dg_chol_cols<2, 1>(r, st, tx, ty, info, gidx0);
+  dg_chol_cols<3, 0>(r, st, tx, ty, info, gidx0);
+  dg_chol_cols<3, 1>(r, st, tx, ty, info, gidx0);
   __syncwarp();
   if (lane == 0) mbar_arrive(colbar + 31);
-  // L out: column c, lane = row (coalesced)
-#pragma unroll 4
-  for (int c = 0; c < 32; ++c) {
-    if (lane > c) __stcg(At + lane + (size_t)c * ld, Ls[lane + c * 33]);
-    if (lane == c) __stcg(At + lane + (size_t)c * ld, dgl[c]);
-  }
-  dv[lane] = dgl[lane];
-  __syncwarp();
 }
 
-__device__ __noinline__ void dg_inv_follow(double* sm0, double* sm_own, int lane, double* St, long lds,
-                                           uint64_t* colbar, uint32_t parity) {
-  double* Ls = sm0;
-  const double* idg = sm0 + 32 * 33 + 96;
-  double* rowbuf = sm_own;  // 2 x 32 in the follower's own stage
-  const int tx = lane & 7, ty = lane >> 3;
-  double r[8][4];
+// Follower: X = L^-1, one COLUMN of X per lane (lane c solves L x = e_c), right-looking and fully unrolled: when column
+// k of L is published, x_k = (delta_kc - acc_k) / L_kk is final and acc_i += L(i, k) x_k for i > k -- 31 - k independent
+// DFMAs fed by broadcast reads of the leader's shared-memory copy of L, accumulators in registers, no cross-lane traffic
+// at all: ~1.5 us of work per tile against the leader's ~6 us, so the inverse is complete right after the last column of
+// the factorisation.  (The first version mirrored the factorisation -- a right-looking update of a register tile with
+// a shared-memory broadcast per row -- and fell 3 us per tile behind once the leader was pipelined; a rolled
+// dot-product form was latency bound on its loads: 6 us behind.)  It also writes the outputs: column k of L and L_kk
+// (coalesced), row k of X into the X (lower) / U (upper) tile.
+__device__ __noinline__ void dg_inv_follow(double* sm0, int lane, double* St, long lds, uint64_t* colbar, uint32_t parity,
+                                           double* At, long ld, double* dv) {
+  const double* Ls = sm0;
+  const double* dgl = sm0 + 32 * 33 + 64;
+  const double* idg = dgl + 32;
+  double acc[32];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+  double* gl = At + lane;         // column k of L at gl + k ld
+  double* gu = St + lane;         // U(c, k) at gu + k lds
+  double* gx = St + (size_t)lane * lds;  // X(k, c) at gx + k
 #pragma unroll
-    for (int b = 0; b < 4; ++b) r[a][b] = (4 * a + ty == 8 * b + tx) ? 1.0 : 0.0;
-  dg_inv_rows<0>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  dg_inv_rows<1>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  dg_inv_rows<2>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  dg_inv_rows<3>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  dg_inv_rows<4>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  dg_inv_rows<5>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  dg_inv_rows<6>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  dg_inv_rows<7>(r, Ls, rowbuf, idg, tx, ty, colbar, parity);
-  __syncwarp();
-  // X (lower) / U (upper) tile out: column c, lane = row.  X(i, c) = U(c, i) = Ls[c + i * 33] for i > c.
-#pragma unroll 4
-  for (int c = 0; c < 32; ++c) {
-    const double v = (lane > c) ? Ls[c + lane * 33] : ((lane == c) ? idg[c] : Ls[lane + c * 33]);
-    __stcg(St + lane + (size_t)c * lds, v);
+  for (int k = 0; k < 32; ++k) {
+    mbar_wait(colbar + k, parity);  // column k of L and 1 / L_kk published by the factoring warp (acquire)
+    const double* lk = Ls + 33 * k;  // L(i, k) at lk[i]
+    {  // column k of L out
+      const double v = (lane > k) ? lk[lane] : dgl[k];
+      if (lane >= k) __stcg(gl + (size_t)k * ld, v);
+      if (lane == k) dv[k] = v;
+    }
+    const double x = (((lane == k) ? 1.0 : 0.0) - acc[k]) * idg[k];
+    if (lane <= k) __stcg(gu + (size_t)k * lds, x);  // U(c, k) = X(k, c), and the diagonal
+    if (lane < k) __stcg(gx + k, x);                 // X(k, c)
+#pragma unroll
+    for (int i = k + 1; i < 32; ++i) acc[i] = fma(lk[i], x, acc[i]);
   }
-  __syncwarp();
 }
 
-// The serial chain of one tile column, run by the warp that will factor tile k+1 (warp 0 of its CTA) right after the
-// barrier that publishes L_kk / X_kk -- it does not wait for the rest of the column solve:
-//   L_(k+1)k = A_(k+1)k X_kk^T        (stored for everybody else; arrives at the second barrier of the step)
-//   A_(k+1)(k+1) -= L_(k+1)k L_(k+1)k^T   (operand straight from the stage, result handed over in shared memory)
-//   Cholesky of the updated tile          (dg_chol_lead, follower one column behind)
-// and only then collects the second barrier.  Round 2's first version ran update + factorisation after that barrier
-// and went through global memory twice: 21.5 us per tile column, of which 10 us were barrier + solve + update.
-__device__ __noinline__ void dg_chain_step(double* stage0, int lane, double* Lk1k, const double* Xkk, long ldx,
-                                           double* Adiag, long ld, double* dv, int* info, int gidx0, uint64_t* colbar,
-                                           long long* dbg) {
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// The serial chain of one tile column, run by FOUR warps of the CTA that will factor tile k+1 (one per SM sub-partition:
+// the leader = warp 0, and three helpers that would otherwise idle) right after the barrier that publishes L_kk / X_kk --
+// they do not wait for the rest of the column solve:
+//   L_(k+1)k = A_(k+1)k X_kk^T            (stored for everybody else; each warp arrives at the step's second barrier)
+//   A_(k+1)(k+1) -= L_(k+1)k L_(k+1)k^T   (operand straight from shared memory, result handed over in shared memory)
+//   Cholesky of the updated tile          (leader only: dg_chol_lead; the follower warp runs one column behind)
+// Each of the four warps owns 8 columns of both products (32 DMMA per product instead of 128 on one warp); operands are
+// staged cooperatively, the three hand-overs are named barriers of 128 threads.  History (profiles/r02/
+// diag_block_timeline.md): update + factorisation after the second barrier, through global memory: 21.5 us per tile
+// column; one warp running this chain: 14.4 us.
+// h = 0 (leader) .. 3.  sA / sB: the leader's stage; sL: a helper's stage.
+__device__ __noinline__ void dg_chain_step(double* stage0, double* sL, int h, int lane, double* Lk1k, const double* Xkk,
+                                           long ldx, double* Adiag, long ld, double* dv, int* info, int gidx0,
+                                           uint64_t* colbar, long long* dbg) {
   using namespace dg;
   const int g = lane >> 2, tq = lane & 3;
   double* sA = stage0;
   double* sB = stage0 + TS * LDT;
-  dg_stage_pair(stage0, Lk1k, ld, Xkk, ldx, lane);
-  double acc[4][4][2];
+  // this warp's 8 columns of the diagonal tile (all updates of earlier columns were complete at the first barrier)
+  double c[4][2];
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int e = 0; e < 2; ++e) c[mt][e] = __ldcg(Adiag + (mt * 8 + g) + (size_t)(8 * h + 2 * tq + e) * ld);
+  {  // cooperative staging: 128 lanes, 4 + 4 16-byte loads each
+    const int tid = h * 32 + lane;
+    double2 va[4], vb[4];
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    const int k = ks * 4 + tq;
-    double a[4], b[4];
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt) a[mt] = sA[mt * 8 + g + k * LDT];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int row = nt * 8 + g;
-      const double v = sB[row + k * LDT];
-      b[nt] = (row >= k) ? v : 0.0;  // X_kk is lower triangular; its upper part holds U
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * 128 + tid, col = idx >> 4, r2 = 2 * (idx & 15);
+      va[q] = __ldcg(reinterpret_cast<const double2*>(Lk1k + r2 + (size_t)col * ld));
+      vb[q] = __ldcg(reinterpret_cast<const double2*>(Xkk + r2 + (size_t)col * ldx));
     }
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+    for (int q = 0; q < 4; ++q) {
+      const int idx = q * 128 + tid, col = idx >> 4, r2 = 2 * (idx & 15);
+      *reinterpret_cast<double2*>(sA + r2 + col * LDT) = va[q];
+      *reinterpret_cast<double2*>(sB + r2 + col * LDT) = vb[q];
+    }
   }
-  __syncwarp();  // everybody is done reading the staged operands
+  named_bar_sync(1, 128);
+  double acc[4][2];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int row = mt * 8 + g, col = nt * 8 + 2 * tq + e;
-        __stcg(Lk1k + row + (size_t)col * ld, acc[mt][nt][e]);
-        sA[row + col * LDT] = acc[mt][nt][e];
-      }
-  cluster_arrive();  // second barrier of the step: L_(k+1)k is published; collected after the factorisation
-  // the diagonal tile (all updates of earlier columns were complete at the first barrier); the accumulators of the
-  // first product are dead by now (two live 32 x 32 fragment sets would not fit 128 registers)
-  double c[4][4][2];
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) c[mt][nt][e] = __ldcg(Adiag + (mt * 8 + g) + (size_t)(nt * 8 + 2 * tq + e) * ld);
-  __syncwarp();
+  for (int mt = 0; mt < 4; ++mt) acc[mt][0] = acc[mt][1] = 0.0;
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
     const int k = ks * 4 + tq;
-    double a[4], b[4];
+    const int row = 8 * h + g;
+    const double bv = sB[row + k * LDT];
+    const double b = (row >= k) ? bv : 0.0;  // X_kk is lower triangular; its upper part holds U
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt) a[mt] = -sA[mt * 8 + g + k * LDT];
+    for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][0], acc[mt][1], sA[mt * 8 + g + k * LDT], b);
+  }
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) b[nt] = sA[nt * 8 + g + k * LDT];
+  for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
+    for (int e = 0; e < 2; ++e) {
+      const int row = mt * 8 + g, col = 8 * h + 2 * tq + e;
+      __stcg(Lk1k + row + (size_t)col * ld, acc[mt][e]);
+      sL[row + col * LDT] = acc[mt][e];
+    }
+  cluster_arrive();  // second barrier of the step: this warp's part of L_(k+1)k is published; collected at the end
+  named_bar_sync(2, 128);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
+  for (int ks = 0; ks < 8; ++ks) {
+    const int k = ks * 4 + tq;
+    const double b = sL[8 * h + g + k * LDT];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) dmma884(c[mt][0], c[mt][1], -sL[mt * 8 + g + k * LDT], b);
   }
   // hand the updated tile to the factorisation's register layout through the B half of the stage (stride 33)
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) sB[(mt * 8 + g) + (nt * 8 + 2 * tq + e) * 33] = c[mt][nt][e];
-  __syncwarp();
-  if (dbg != nullptr && lane == 0) dbg[1] = clock64();
-  dg_chol_lead<true>(stage0, lane, Adiag, ld, sB, dv, info, gidx0, colbar);
-  if (dbg != nullptr && lane == 0) dbg[2] = clock64();
+    for (int e = 0; e < 2; ++e) sB[(mt * 8 + g) + (8 * h + 2 * tq + e) * 33] = c[mt][e];
+  if (h == 0) {
+    named_bar_sync(3, 128);
+    if (dbg != nullptr && lane == 0) dbg[1] = clock64();
+    dg_chol_lead<true>(stage0, lane, Adiag, ld, sB, dv, info, gidx0, colbar);
+    if (dbg != nullptr && lane == 0) dbg[2] = clock64();
+  } else {
+    named_bar_arrive(3, 128);
+  }
   cluster_wait();
 }
 
@@ -491,7 +507,7 @@ __global__ void __launch_bounds__(dg::THREADS, 2) diag_block_kernel(const DiagAr
     dg_chol_lead<false>(stage0, lane, At(0, 0), ld, nullptr, dv, a.info, a.blk0 * 128, colbar);
     stampF(0, 2);
   } else if (gw == fw(0) + NC) {
-    dg_inv_follow(stage0, stage, lane, St(0, 0), N, colbar, 0u);
+    dg_inv_follow(stage0, lane, St(0, 0), N, colbar, 0u, At(0, 0), ld, dv);
   }
 #pragma unroll 1
   for (int k = 0; k < nt; ++k) {
@@ -500,26 +516,38 @@ __global__ void __launch_bounds__(dg::THREADS, 2) diag_block_kernel(const DiagAr
     stampT(k, 1);
     const bool more = (k + 1 < nt);
     const int f = fw(k + 1);  // CTA rank of the warps that factor tile k+1 (warp 0: Cholesky, warp 1: inverse)
-    if (more && gw == f) {
-      // the serial chain: solve L_(k+1)k, update and factor tile k+1 (arrives at the second barrier on the way)
-      stampF(k + 1, 0);
-      dg_chain_step(stage0, lane, At(k + 1, k), St(k, k), N, At(k + 1, k + 1), ld, dv + (k + 1) * TS, a.info,
-                    a.blk0 * 128 + (k + 1) * TS, colbar, a.dbg ? a.dbg + 8 * (k + 1) + 5 : nullptr);
-      continue;
-    }
-    if (more && gw == f + NC) {
-      cluster_arrive();
-      dg_inv_follow(stage0, stage, lane, St(k + 1, k + 1), N, colbar, (uint32_t)(((k + 1) / NC) & 1));
-      cluster_wait();
-      continue;
+    if (more && crank == f) {
+      // the serial chain: warps 0, 5, 2, 3 of the factoring CTA (one per SM sub-partition) solve L_(k+1)k and update
+      // tile k+1, warp 0 factors it, warp 1 inverts it one column behind; all of them arrive at the second barrier on
+      // the way and collect it when they are done
+      const int h = (warp == 0) ? 0 : (warp == 5) ? 1 : (warp == 2) ? 2 : (warp == 3) ? 3 : -1;
+      if (h >= 0) {
+        if (h == 0) stampF(k + 1, 0);
+        dg_chain_step(stage0, stage0 + 2 * STAGE, h, lane, At(k + 1, k), St(k, k), N, At(k + 1, k + 1), ld,
+                      dv + (k + 1) * TS, a.info, a.blk0 * 128 + (k + 1) * TS, colbar,
+                      a.dbg ? a.dbg + 8 * (k + 1) + 5 : nullptr);
+        continue;
+      }
+      if (warp == 1) {
+        cluster_arrive();
+        dg_inv_follow(stage0, lane, St(k + 1, k + 1), N, colbar, (uint32_t)(((k + 1) / NC) & 1),
+                      At(k + 1, k + 1), ld, dv + (k + 1) * TS);
+        cluster_wait();
+        continue;
+      }
     }
     // column k of L: L_ik = A_ik X_kk^T (in place), i > k+1, and row k of X: X(k, j) = -X_kk AccT(j, k)^T,
     // U(j, k) = X(k, j)^T -- dealt over the warps that are not on the chain
     {
+      constexpr int NWK = (NC - 1) * WARPS;        // warps of the other CTAs
       const int skip = more ? 1 : 0;               // tile (k+1, k) belongs to the chain
       const int nsolve = nt - 1 - k - skip;
-      const int nw = more ? GW - 2 : GW;
-      const int me = more ? gw - (gw > f) - (gw > f + NC) : gw;
+      const int nw = more ? NWK + 3 : GW;
+      int me = gw;
+      if (more) {
+        if (crank != f) me = warp * (NC - 1) + (crank - f - 1 + NC) % NC;  // CTA index fastest
+        else me = NWK + ((warp == 4) ? 0 : (warp == 6) ? 1 : 2);           // warps 4, 6, 7 of the chain CTA
+      }
       for (int u = me; u < nsolve + k; u += nw) {
         if (u < nsolve) {
           const int i = k + 1 + skip + u;
