@@ -374,14 +374,19 @@ inline int trtri_merge_range(const DenseWork& w, int lo, int hi, cudaStream_t st
 
 // Diagonal block [j0, j1) of the panel schedule: L_JJ, X_JJ = L_JJ^-1 (lower 128-blocks), U_JJ (upper), DX / DU tiles,
 // dvec.  One cluster launch (diag_block.cuh), or the leaf recursion followed by the early merge levels.
-inline int diag_block_factor_invert(const DenseWork& w, int j0, int j1, cudaStream_t st) {
+// `share` = how many ranks split the trailing work (1 on a single GPU): the 16-CTA cluster halves the block's latency
+// but has to gather 16 free SMs of one GPC, which costs throughput while the trailing updates still fill the GPU
+// (C3 on one GPU: 89.1 ms with 8 CTAs, 90.5 with 16); it is used once the remaining trailing matrix per rank is
+// small enough for the chain of diagonal blocks to bound the factorisation.
+inline int diag_block_factor_invert(const DenseWork& w, int j0, int j1, cudaStream_t st, int share = 1) {
   if (w.diag_ws != nullptr) {
     DiagArgs a{};
     a.A = w.A; a.ld = w.ld; a.blk0 = j0; a.nblk = j1 - j0; a.DX = w.DX; a.DU = w.DU; a.dvec = w.dvec; a.info = w.info;
     a.S = w.diag_ws;
     a.W = w.diag_ws + (size_t)w.panel_blocks * TB * w.panel_blocks * TB;
     a.dbg = w.diag_dbg;
-    return launch_diag_block(a, st);
+    const long rest = (long)(w.nb - j1) * TB;  // rows below this block
+    return launch_diag_block(a, st, rest <= 6144L * share);
   }
   ACE_TRY(potrf_rec(w, j0, j1, st));
   return trtri_merge_range(w, j0, j1, st, w.Wsmall);

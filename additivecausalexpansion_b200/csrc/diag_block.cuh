@@ -240,6 +240,10 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], DgCholState& st,
 #pragma unroll
         for (int a = A0; a < 8; ++a) cn[4 * a] = r[a][JB];
       }
+      // keep the rest of the update BEHIND the hand-over (the compiler otherwise hoists these independent DFMAs above
+      // the divergent store block and the pipelining is lost)
+#pragma unroll
+      for (int b = JB + 1; b < 4; ++b) asm volatile("" : "+d"(cm[b]) : : "memory");
 #pragma unroll
       for (int b = JB + 1; b < 4; ++b)
 #pragma unroll
@@ -252,6 +256,8 @@ __device__ __forceinline__ void dg_chol_cols(double (&r)[8][4], DgCholState& st,
 #pragma unroll
         for (int a = A0; a < 8; ++a) cn[4 * a] = r[a][JN];
       }
+#pragma unroll
+      for (int b = JN + 1; b < 4; ++b) asm volatile("" : "+d"(cm[b]) : : "memory");
 #pragma unroll
       for (int b = JN + 1; b < 4; ++b)
 #pragma unroll
@@ -674,9 +680,15 @@ inline int configure_diag_kernel() {
   return 0;
 }
 
-inline int launch_diag_block(const DiagArgs& a, cudaStream_t st) {
+// wide: use the 16-CTA cluster when the device accepts it (ACE_DIAG_CLUSTER=8 / 16 forces one size)
+inline int launch_diag_block(const DiagArgs& a, cudaStream_t st, bool wide = true) {
   if (diag_cluster_size() == 0) ACE_TRY(configure_diag_kernel());
-  return diag_cluster_size() == 16 ? launch_diag_block_nc<16>(a, st) : launch_diag_block_nc<8>(a, st);
+  static const int forced = [] {
+    const char* e = std::getenv("ACE_DIAG_CLUSTER");
+    return e ? std::atoi(e) : 0;
+  }();
+  const bool use16 = diag_cluster_size() == 16 && (forced == 16 || (forced == 0 && wide));
+  return use16 ? launch_diag_block_nc<16>(a, st) : launch_diag_block_nc<8>(a, st);
 }
 
 }  // namespace ace

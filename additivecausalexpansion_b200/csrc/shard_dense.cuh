@@ -171,7 +171,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     }
     tr.mark(J, 0, w.side);
     if (mine) {
-      ACE_TRY(diag_block_factor_invert(w, j0, j1, w.side));  // L_JJ, X_JJ / U_JJ in place
+      ACE_TRY(diag_block_factor_invert(w, j0, j1, w.side, cx.world));  // L_JJ, X_JJ / U_JJ in place
       ACE_CUDA(cudaMemcpy2DAsync(Hd, sizeof(double) * hJ, blkptr(w, j0, j0), sizeof(double) * w.ld,
                                  sizeof(double) * wJ, (size_t)wJ, cudaMemcpyDeviceToDevice, w.side));
       if (wN > 0) {
