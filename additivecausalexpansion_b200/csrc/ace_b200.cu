@@ -20,6 +20,7 @@
 #include "pair_kernels.cuh"
 #include "grad2_kernel.cuh"
 #include "grad3_kernel.cuh"
+#include "kernmat2_kernel.cuh"
 #include "pred_kernels.cuh"
 
 namespace ace {
@@ -128,6 +129,41 @@ __global__ void synth_spd_kernel(double* A, long ld, int n) {
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
+// The exact-shape pair kernels (grad3_kernel.cuh, kernmat2_kernel.cuh) read lambda_b and the length-scale weights from
+// a __constant__ table, one per module: [wait for the previous user's kernel] -> copy -> kernel -> [record], enqueued
+// under a per-device lock, serialises the launches of different fit handles that use the same table on one device (all
+// other work of the handles still overlaps).  Inside a stream capture the wait / record become external event nodes,
+// so graph replays of different handles are ordered the same way.
+struct ConstChain {
+  std::mutex mu;
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+};
+static ConstChain& const_chain(int which, int dev) {
+  static ConstChain chains[2][64];
+  return chains[which][dev & 63];
+}
+template <class F>
+static int with_const_chain(int which, cudaStream_t st, F&& launch) {
+  int dev = 0;
+  ACE_CUDA(cudaGetDevice(&dev));
+  ConstChain& ch = const_chain(which, dev);
+  std::lock_guard<std::mutex> lk(ch.mu);
+  if (ch.ev == nullptr) ACE_CUDA(cudaEventCreateWithFlags(&ch.ev, cudaEventDisableTiming));
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  ACE_CUDA(cudaStreamIsCapturing(st, &cs));
+  const bool cap = cs != cudaStreamCaptureStatusNone;
+  if (ch.recorded) ACE_CUDA(cudaStreamWaitEvent(st, ch.ev, cap ? cudaEventWaitExternal : cudaEventWaitDefault));
+  ACE_TRY(launch());
+  ACE_CUDA(cudaEventRecordWithFlags(ch.ev, st, cap ? cudaEventRecordExternal : cudaEventRecordDefault));
+  ch.recorded = true;
+  return 0;
+}
+
+// launchers exported by the pair_kernmat2.cu objects (one per kernel kind)
+int launch_kernmat2_k0(const KernArgs&, unsigned, size_t, cudaStream_t);
+int launch_kernmat2_k1(const KernArgs&, unsigned, size_t, cudaStream_t);
+
 static int launch_kernmat(const KernArgs& a, int kind, cudaStream_t st) {
   const int B = a.B;
   if (B < 1 || B > BMAXT || a.p < 1 || a.p > PMAX) {
@@ -145,6 +181,17 @@ static int launch_kernmat(const KernArgs& a, int kind, cudaStream_t st) {
     grid = (unsigned)(T * (T + 1) / 2);
   } else {
     grid = (unsigned)((a.n1_pad / kb::T) * (a.n2_pad / kb::T));
+  }
+  // kernmat2_kernel: exact number of terms, weights in constant memory, lock-step sqrt / exp (B <= 16, p <= 32)
+  static const int impl = [] {
+    const char* e = std::getenv("ACE_KERNMAT_IMPL");
+    return e ? std::atoi(e) : 2;
+  }();
+  if (impl == 2 && B <= G3_LAM && a.p <= G3_PD) {
+    const size_t smem2 = kb2::smem_bytes(a.p, B - 1, a.sym != 0);
+    return with_const_chain(1, st, [&]() -> int {
+      return kind == 0 ? launch_kernmat2_k0(a, grid, smem2, st) : launch_kernmat2_k1(a, grid, smem2, st);
+    });
   }
   auto go = [&](auto kern) -> int {
     ACE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -289,17 +336,6 @@ static int launch_grad_t(const GradArgs& a, int kind, const GradPlan& pl, cudaSt
 
 static int launch_grad2(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st);
 
-// per-device ordering of the launches that use grad3's constant-memory table (see launch_grad)
-struct G3Chain {
-  std::mutex mu;
-  cudaEvent_t ev = nullptr;
-  bool recorded = false;
-};
-static G3Chain& g3_chain(int dev) {
-  static G3Chain chains[64];
-  return chains[dev & 63];
-}
-
 static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStream_t st) {
   if (pl.v3) {
     auto go = [&](int cw) -> int {
@@ -315,23 +351,7 @@ static int launch_grad(const GradArgs& a, int kind, const GradPlan& pl, cudaStre
       }
     };
     if (!pl.cw3) return go(0);
-    // The constant-memory table is one per module: [wait for the previous user's kernel] -> copy -> kernel -> [record],
-    // enqueued under a per-device lock, serialises the gradient launches of different fit handles on one device
-    // (all other work of the handles still overlaps).  Inside a stream capture the wait / record become external
-    // event nodes, so graph replays of different handles are ordered the same way.
-    int dev = 0;
-    ACE_CUDA(cudaGetDevice(&dev));
-    G3Chain& ch = g3_chain(dev);
-    std::lock_guard<std::mutex> lk(ch.mu);
-    if (ch.ev == nullptr) ACE_CUDA(cudaEventCreateWithFlags(&ch.ev, cudaEventDisableTiming));
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    ACE_CUDA(cudaStreamIsCapturing(st, &cs));
-    const bool cap = cs != cudaStreamCaptureStatusNone;
-    if (ch.recorded) ACE_CUDA(cudaStreamWaitEvent(st, ch.ev, cap ? cudaEventWaitExternal : cudaEventWaitDefault));
-    ACE_TRY(go(1));
-    ACE_CUDA(cudaEventRecordWithFlags(ch.ev, st, cap ? cudaEventRecordExternal : cudaEventRecordDefault));
-    ch.recorded = true;
-    return 0;
+    return with_const_chain(0, st, [&]() -> int { return go(1); });
   }
   if (pl.v2) return launch_grad2(a, kind, pl, st);
   switch (pl.PD) {

@@ -47,6 +47,26 @@ __device__ __forceinline__ double term_value(int b, double lam, double D_or_r, d
   }
 }
 
+struct KernArgs {
+  const double *X1, *Z1, *LZ1;  // row points    (n1, ld1)
+  const double *X2, *Z2, *LZ2;  // column points (n2, ld2)
+  long ld1, ld2;
+  int n1, n2, n1_pad, n2_pad, p, B;
+  const double* tab;
+  double* K;        // n1_pad x n2_pad, ldk
+  long ldk;
+  double* cube;     // optional: B slices of (ldk x n2_pad)
+  long cube_slice;
+  int sym;          // 1: X1 == X2, lower tiles computed and mirrored, exactly symmetric output
+  int add_noise;    // sym: K_ii += e^sigma for i < n
+  int pad_identity; // sym: rows/cols >= n form an identity block
+  int skip0;        // 1: leave the nuisance term b = 0 out of the sum (marginal kernels, src/pred_cpp.cpp:55-63)
+  // rectangular blocks of the TRAINING kernel (multi-GPU column-block sharding): global index of the
+  // block's first row / column, so that the noise diagonal and the identity padding land where they
+  // belong.  Both 0 and add_noise = pad_identity = 0 for ordinary cross kernels.
+  int row_off, col_off;
+};
+
 struct GradArgs {
   const double *X, *Z, *LZ;  // n_pad x p, n_pad x Bz (ld = ldx)
   long ldx;
