@@ -404,12 +404,15 @@ struct Core {
   cudaStream_t bulk = nullptr; // bulk panel pieces: own stream (and communicator)
   int rank_lo() const { return shard_emulate ? 0 : shard_rank; }
   int rank_hi() const { return shard_emulate ? shard_world : shard_rank + 1; }
-  ShardCtx shard_ctx(ncclComm_t comm, ncclComm_t comm2) const {
+  DBuf<double> mid0, mid1;     // early copies of the first bulk block (shard_dense.cuh: mid)
+  cudaStream_t mids = nullptr;
+  ShardCtx shard_ctx(ncclComm_t comm, ncclComm_t comm2, ncclComm_t comm3 = nullptr) const {
     ShardCtx cx;
     cx.rank = shard_rank; cx.world = shard_world; cx.emulate = shard_emulate; cx.comm = comm; cx.h_min = shard_hmin;
     cx.comm2 = comm2;
     cx.events = const_cast<cudaEvent_t*>(shard_events.data());
     cx.head[0] = head0.p; cx.head[1] = head1.p; cx.bulk_stream = bulk;
+    cx.comm3 = comm3; cx.mid[0] = mid0.p; cx.mid[1] = mid1.p; cx.mid_stream = mids;
     cx.incr = shard_incr;
     return cx;
   }
@@ -438,6 +441,18 @@ struct Core {
           int lo = 0, hi = 0;
           ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
           ACE_CUDA(cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, hi));
+        }
+        {
+          const char* sm = std::getenv("ACE_SHARD_MID");
+          if (!(sm && std::atoi(sm) == 0)) {
+            ACE_TRY(mid0.alloc(pw * pw));
+            ACE_TRY(mid1.alloc(pw * pw));
+            if (!mids) {
+              int lo = 0, hi = 0;
+              ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+              ACE_CUDA(cudaStreamCreateWithPriority(&mids, cudaStreamNonBlocking, hi));
+            }
+          }
         }
         const int NP = shard_panels(n_pad / TB, panel_blocks);
         while ((int)shard_events.size() < SHARD_EVENT_KINDS * NP) {
@@ -477,6 +492,7 @@ struct Core {
       if (e) cudaEventDestroy(e);
     for (auto& e : shard_events) cudaEventDestroy(e);
     if (bulk) cudaStreamDestroy(bulk);
+    if (mids) cudaStreamDestroy(mids);
     if (st) cudaStreamDestroy(st);
     if (side) cudaStreamDestroy(side);
     if (aux) cudaStreamDestroy(aux);
@@ -728,9 +744,10 @@ struct ace_fit {
   cudaGraphExec_t gexec = nullptr;
   double iter_dev = 0.0;  // host shadow of sc[SC_ITER]
   double ms[6] = {0, 0, 0, 0, 0, 0};
-  ncclComm_t comm = nullptr, comm2 = nullptr;  // multi-GPU sharded mode
+  ncclComm_t comm = nullptr, comm2 = nullptr, comm3 = nullptr;  // multi-GPU sharded mode
   ~ace_fit() {
     if (comm2 && nccl_api().ok) nccl_api().CommDestroy(comm2);
+    if (comm3 && nccl_api().ok) nccl_api().CommDestroy(comm3);
     if (comm && nccl_api().ok) nccl_api().CommDestroy(comm);
     if (sw0) cudaEventDestroy(sw0);
     if (sw1) cudaEventDestroy(sw1);
@@ -780,7 +797,7 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
     ACE_TRY(c.enqueue_alpha(c.Bf.p, 1));
   } else {
     // redundant Cholesky (ms[1]), then the split triangular inverse (ms[2]) and this rank's tiles of U U^T (ms[3])
-    const ShardCtx cx = c.shard_ctx(f->comm, f->comm2);
+    const ShardCtx cx = c.shard_ctx(f->comm, f->comm2, f->comm3);
     if (spotrf) {
       ACE_TRY(potrf_sharded(w, cx));
     } else {
@@ -1065,6 +1082,19 @@ int ace_fit_shard(ace_fit* f, const char* id128, int rank, int world) {
     ACE_CUDA(cudaMemcpyAsync(&id2, box.p, 128, cudaMemcpyDeviceToHost, c.st));
     ACE_CUDA(cudaStreamSynchronize(c.st));
     ACE_NCCL(nc.CommInitRank(&f->comm2, world, id2, rank));
+  }
+  {  // third communicator (early first bulk block), same way
+    ncclUniqueId id3;
+    DBuf<double> box;
+    ACE_TRY(box.alloc(16));
+    if (rank == 0) {
+      ACE_NCCL(nc.GetUniqueId(&id3));
+      ACE_CUDA(cudaMemcpyAsync(box.p, &id3, 128, cudaMemcpyHostToDevice, c.st));
+    }
+    ACE_NCCL(nc.Broadcast(box.p, box.p, 16, ncclFloat64, 0, f->comm, c.st));
+    ACE_CUDA(cudaMemcpyAsync(&id3, box.p, 128, cudaMemcpyDeviceToHost, c.st));
+    ACE_CUDA(cudaStreamSynchronize(c.st));
+    ACE_NCCL(nc.CommInitRank(&f->comm3, world, id3, rank));
   }
   c.shard_rank = rank;
   c.shard_world = world;

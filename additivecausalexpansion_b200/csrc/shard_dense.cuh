@@ -44,6 +44,11 @@ struct ShardCtx {
   cudaEvent_t* events = nullptr;    // SHARD_EVENT_KINDS * panels events of potrf_sharded
   double* head[2] = {nullptr, nullptr};  // packed panel heads, (2 * panel width) x (panel width) doubles each
   cudaStream_t bulk_stream = nullptr;
+  // third piece of a panel: the FIRST block of the bulk, L[J+2 rows, J], sent early on its own stream and communicator
+  // (see potrf_sharded); packed (panel width)^2 doubles each
+  ncclComm_t comm3 = nullptr;
+  double* mid[2] = {nullptr, nullptr};
+  cudaStream_t mid_stream = nullptr;
   bool incr = false;  // incremental inverse behind the panels: every rank grows X[:, its column panels] in the background
   bool mine(int panel) const { return emulate || panel % world == rank; }
 };
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(256) splitk_sum_kernel(const double* __restric
   out[idx] = acc;
 }
 
-constexpr int SHARD_EVENT_KINDS = 7;
+constexpr int SHARD_EVENT_KINDS = 8;
 
 // ACE_SHARD_TRACE=1: per-panel timeline of potrf_sharded (CUDA events with timing), printed by shard_trace_dump
 struct ShardTrace {
@@ -135,6 +140,11 @@ inline void shard_trace_dump(int rank) {
 //             high-priority stream -> chain per panel = diagonal factorisation + one small GEMM + one small broadcast.
 //   bulk(J) = the rows below, needed only when the next head is solved, i.e. one diagonal factorisation later; own
 //             stream and communicator, so the two transfers never queue behind each other.
+//   mid(J)  = the first block of the bulk, L[J+2 rows, J], sent a second time and EARLY (third stream and
+//             communicator): it is all that head(J+1) needs of bulk(J) (the update of A[J+2 rows, J+1]).  Without it
+//             the whole bulk transfer (46 MB at panel 8 of C3, 0.3 ms) and its look-ahead GEMM sat on the serial chain:
+//             0.75 ms per panel on 8 GPUs against 0.25 ms for diagonal block + head (profiles/r02/shard_trace_w8.log).
+//             mid(J) itself needs the look-ahead of bulk(J-1), so the bulk path now has a whole panel period of slack.
 inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
   const int nb = w.nb, pb = w.panel_blocks, NP = shard_panels(nb, pb);
   if (!w.Wp[0] || !cx.events || !cx.head[0] || !cx.bulk_stream) {
@@ -148,12 +158,16 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
   cudaEvent_t* ev_step = cx.events + 4 * NP;   // main : panel J applied to all my panels
   cudaEvent_t* ev_copy = cx.events + 5 * NP;   // aux  : panel J copied into A
   cudaEvent_t* ev_diag = cx.events + 6 * NP;   // side : head(J) applied to the diagonal block of panel J+1
+  cudaEvent_t* ev_midla = cx.events + 7 * NP;  // mid  : mid(J) applied to A[J+2 rows, J+1] (look-ahead, first block)
+  const bool use_mid = cx.mid[0] != nullptr && cx.mid_stream != nullptr && (cx.emulate || cx.comm3 != nullptr);
+  cudaStream_t mids = cx.mid_stream;
   NcclApi& nc = nccl_api();
   cudaStream_t bulk = cx.bulk_stream;
   ACE_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int), w.main));
   ACE_CUDA(cudaEventRecord(w.ev_upd[1], w.main));  // fork: the other streams join after everything queued on main
   ACE_CUDA(cudaStreamWaitEvent(w.side, w.ev_upd[1], 0));
   ACE_CUDA(cudaStreamWaitEvent(bulk, w.ev_upd[1], 0));
+  if (use_mid) ACE_CUDA(cudaStreamWaitEvent(mids, w.ev_upd[1], 0));
   ACE_CUDA(cudaStreamWaitEvent(w.aux, w.ev_upd[1], 0));
   shard_trace_begin(NP, w.main);
   ShardTrace& tr = shard_trace();
@@ -161,12 +175,16 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     const int j0 = J * pb, j1 = std::min(j0 + pb, nb), j2 = std::min(j1 + pb, nb);
     const long wJ = (long)(j1 - j0) * TB, wN = (long)(j2 - j1) * TB;  // panel width, next panel's width
     const long hJ = wJ + wN, mB = (long)(nb - j2) * TB;               // head rows, bulk rows
+    const int j3 = std::min(j2 + pb, nb);
+    const long wM = use_mid ? (long)(j3 - j2) * TB : 0;               // mid rows (first block of the bulk)
     double* Hd = cx.head[J & 1];
     double* Wp = w.Wp[J & 1];
+    double* Md = cx.mid[J & 1];
     const bool mine = cx.mine(J), la = (J + 1 < NP) && cx.mine(J + 1);
     // ================= head(J): side stream, communicator `comm`
     if (J >= 2) {  // head buffer free: its readers were side (in order), the bulk look-ahead and the copy-out of J-2
       ACE_CUDA(cudaStreamWaitEvent(w.side, ev_la[J - 2], 0));
+      if (use_mid) ACE_CUDA(cudaStreamWaitEvent(w.side, ev_midla[J - 2], 0));
       ACE_CUDA(cudaStreamWaitEvent(w.side, ev_copy[J - 2], 0));
     }
     tr.mark(J, 0, w.side);
@@ -175,7 +193,8 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
       ACE_CUDA(cudaMemcpy2DAsync(Hd, sizeof(double) * hJ, blkptr(w, j0, j0), sizeof(double) * w.ld,
                                  sizeof(double) * wJ, (size_t)wJ, cudaMemcpyDeviceToDevice, w.side));
       if (wN > 0) {
-        if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(w.side, ev_la[J - 1], 0));  // rows below my diagonal block are up to date
+        // the next panel's rows of my panel are up to date: that block received panel J-1 through mid(J-1)
+        if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(w.side, use_mid ? ev_midla[J - 1] : ev_la[J - 1], 0));
         GemmNT t{};
         t.A = blkptr(w, j1, j0); t.lda = w.ld;
         t.B = blkptr(w, j0, j0); t.ldb = w.ld; t.b_tri = 2; t.Bdiag = w.DX + (size_t)j0 * TB * TB;
@@ -230,18 +249,44 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     }
     ACE_CUDA(cudaEventRecord(ev_bulk[J], bulk));
     tr.mark(J, 5, bulk);
-    if (la && mB > 0) {  // rows below the next panel's diagonal block: A[j2:, J+1] -= bulk * Hn^T
+    if (la && mB > wM) {  // rows below the next panel's diagonal block (and below mid): A[j3:, J+1] -= bulk * Hn^T
       if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(bulk, ev_first[J - 1], 0));
       GemmNT g{};
-      g.A = Wp; g.lda = mB; g.B = Hd + wJ; g.ldb = hJ; g.C = blkptr(w, j2, j1); g.ldc = w.ld;
-      g.M = (int)mB; g.N = (int)wN; g.K = (int)wJ; g.alpha = -1.0; g.beta = 1.0;
+      g.A = Wp + wM; g.lda = mB; g.B = Hd + wJ; g.ldb = hJ; g.C = blkptr(w, j2, j1) + wM; g.ldc = w.ld;
+      g.M = (int)(mB - wM); g.N = (int)wN; g.K = (int)wJ; g.alpha = -1.0; g.beta = 1.0;
       ACE_TRY(launch_gemm_nt(g, bulk));
     }
     ACE_CUDA(cudaEventRecord(ev_la[J], bulk));
     tr.mark(J, 6, bulk);
+    // ================= mid(J): rows [j2, j3), mid stream, communicator `comm3`
+    if (use_mid) {
+      ACE_CUDA(cudaStreamWaitEvent(mids, ev_head[J], 0));  // X_JJ (owner) / head data (look-ahead apply below)
+      if (wM > 0) {
+        if (mine) {
+          // these rows of my panel received panel J-1 with the rest of its bulk (and everything older before that)
+          if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(mids, ev_la[J - 1], 0));
+          GemmNT t{};
+          t.A = blkptr(w, j2, j0); t.lda = w.ld;
+          t.B = blkptr(w, j0, j0); t.ldb = w.ld; t.b_tri = 2; t.Bdiag = w.DX + (size_t)j0 * TB * TB;
+          t.C = Md; t.ldc = wM;
+          t.M = (int)wM; t.N = (int)wJ; t.K = (int)wJ; t.alpha = 1.0; t.beta = 0.0;
+          ACE_TRY(launch_gemm_nt(t, mids));
+        }
+        if (!cx.emulate) ACE_NCCL(nc.Broadcast(Md, Md, (size_t)wM * wJ, ncclFloat64, J % cx.world, cx.comm3, mids));
+        if (la) {  // A[j2:j3, J+1] -= mid * Hn^T
+          if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(mids, ev_first[J - 1], 0));
+          GemmNT g{};
+          g.A = Md; g.lda = wM; g.B = Hd + wJ; g.ldb = hJ; g.C = blkptr(w, j2, j1); g.ldc = w.ld;
+          g.M = (int)wM; g.N = (int)wN; g.K = (int)wJ; g.alpha = -1.0; g.beta = 1.0;
+          ACE_TRY(launch_gemm_nt(g, mids));
+        }
+      }
+      ACE_CUDA(cudaEventRecord(ev_midla[J], mids));
+    }
     // ================= aux stream: the panel into this rank's A (the owner already has its diagonal block)
     ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_head[J], 0));
     ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_bulk[J], 0));
+    if (use_mid) ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_midla[J], 0));  // mid's TRSM has read A[j2:j3, J]
     {
       const long skip = mine ? wJ : 0;
       if (hJ > skip)
@@ -359,6 +404,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
   }
   ACE_CUDA(cudaStreamWaitEvent(w.main, ev_diag[NP - 1], 0));
   ACE_CUDA(cudaStreamWaitEvent(w.main, ev_la[NP - 1], 0));
+  if (use_mid) ACE_CUDA(cudaStreamWaitEvent(w.main, ev_midla[NP - 1], 0));
   ACE_CUDA(cudaStreamWaitEvent(w.main, ev_copy[NP - 1], 0));
   if (!cx.emulate)  // a failed pivot anywhere is everybody's failure
     ACE_NCCL(nc.AllReduce(w.info, w.info, 1, ncclInt32, ncclMax, cx.comm, w.main));
