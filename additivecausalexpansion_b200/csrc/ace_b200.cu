@@ -5,6 +5,7 @@
 #include "../../include/ace_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -404,6 +405,7 @@ struct Core {
   cudaStream_t bulk = nullptr; // bulk panel pieces: own stream (and communicator)
   int rank_lo() const { return shard_emulate ? 0 : shard_rank; }
   int rank_hi() const { return shard_emulate ? shard_world : shard_rank + 1; }
+  DBuf<double> chain_ws;       // split-K partials of the chain's small GEMMs (shard_dense.cuh: chain_gemm)
   DBuf<double> mid0, mid1;     // early copies of the first bulk block (shard_dense.cuh: mid)
   cudaStream_t mids = nullptr;
   ShardCtx shard_ctx(ncclComm_t comm, ncclComm_t comm2, ncclComm_t comm3 = nullptr) const {
@@ -412,6 +414,7 @@ struct Core {
     cx.comm2 = comm2;
     cx.events = const_cast<cudaEvent_t*>(shard_events.data());
     cx.head[0] = head0.p; cx.head[1] = head1.p; cx.bulk_stream = bulk;
+    cx.chain_ws = chain_ws.p;
     cx.comm3 = comm3; cx.mid[0] = mid0.p; cx.mid[1] = mid1.p; cx.mid_stream = mids;
     cx.incr = shard_incr;
     return cx;
@@ -441,6 +444,10 @@ struct Core {
           int lo = 0, hi = 0;
           ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
           ACE_CUDA(cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, hi));
+        }
+        {
+          const char* sk = std::getenv("ACE_SHARD_SPLITK");
+          if (!(sk && std::atoi(sk) == 0)) ACE_TRY(chain_ws.alloc(4 * pw * pw));
         }
         {
           const char* sm = std::getenv("ACE_SHARD_MID");
@@ -799,7 +806,12 @@ static int enqueue_iteration(ace_fit* f, bool timed) {
     // redundant Cholesky (ms[1]), then the split triangular inverse (ms[2]) and this rank's tiles of U U^T (ms[3])
     const ShardCtx cx = c.shard_ctx(f->comm, f->comm2, f->comm3);
     if (spotrf) {
+      static const bool host_time = std::getenv("ACE_SHARD_HOSTTIME") != nullptr;
+      const auto h0 = std::chrono::steady_clock::now();
       ACE_TRY(potrf_sharded(w, cx));
+      if (host_time)
+        std::fprintf(stderr, "[rank %d] potrf_sharded: host enqueue %.3f ms\n", c.shard_rank,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
     } else {
       const int s = potrf_blocked(w);
       if (s < 0) return s;

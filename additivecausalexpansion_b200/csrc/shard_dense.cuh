@@ -49,6 +49,7 @@ struct ShardCtx {
   ncclComm_t comm3 = nullptr;
   double* mid[2] = {nullptr, nullptr};
   cudaStream_t mid_stream = nullptr;
+  double* chain_ws = nullptr;  // split-K partials of the chain's small GEMMs (chain_gemm): 4 x (panel width)^2 doubles
   bool incr = false;  // incremental inverse behind the panels: every rank grows X[:, its column panels] in the background
   bool mine(int panel) const { return emulate || panel % world == rank; }
 };
@@ -67,12 +68,42 @@ __global__ void __launch_bounds__(256) splitk_sum_kernel(const double* __restric
   out[idx] = acc;
 }
 
+// C (ld ldc) = beta * C + sum of the S split-K partials (each R x Cc, packed)
+__global__ void __launch_bounds__(256) splitk_sum_ld_kernel(const double* __restrict__ part, int S, int R, int Cc,
+                                                            double* __restrict__ C, long ldc, double beta) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x, len = (size_t)R * Cc;
+  if (idx >= len) return;
+  double acc = part[idx];
+  for (int s2 = 1; s2 < S; ++s2) acc += part[(size_t)s2 * len + idx];
+  double* dst = C + (idx % R) + (idx / R) * ldc;
+  *dst = (beta != 0.0) ? fma(beta, *dst, acc) : acc;
+}
+
+// A small GEMM of the serial panel chain (head TRSM, diagonal-block update: 512^3) next to the trailing updates of
+// other panels: its 32 tiles of 128 x 64 x 512 share their SMs with a resident update CTA and take ~70 us each, 0.18 ms
+// per launch on the chain (profiles/r02/shard_trace_w8.log).  Split over K into chunks of 128 the 128 shorter CTAs
+// finish in a quarter of that; the partials are summed into C by one small kernel.
+inline int chain_gemm(GemmNT g, double* ws, cudaStream_t st) {
+  const int S = g.K / TB;
+  if (ws == nullptr || S <= 1 || g.K % TB || g.batch > 1 || g.ksplit > 1) return launch_gemm_nt(g, st);
+  double* C = g.C;
+  const long ldc = g.ldc;
+  const double beta = g.beta;
+  g.C = ws; g.ldc = g.M; g.beta = 0.0;
+  g.ksplit = S; g.klen = TB; g.sA = 0; g.sB = 0; g.sC = (long)g.M * g.N;
+  ACE_TRY(launch_gemm_nt(g, st));
+  const size_t len = (size_t)g.M * g.N;
+  splitk_sum_ld_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(ws, S, g.M, g.N, C, ldc, beta);
+  ACE_CUDA(cudaGetLastError());
+  return 0;
+}
+
 constexpr int SHARD_EVENT_KINDS = 8;
 
 // ACE_SHARD_TRACE=1: per-panel timeline of potrf_sharded (CUDA events with timing), printed by shard_trace_dump
 struct ShardTrace {
   cudaEvent_t t0 = nullptr;
-  std::vector<cudaEvent_t> ev;  // 9 per panel: s0 s1 s2 s3 | b1 b2 b3 | m0 m1
+  std::vector<cudaEvent_t> ev;  // 14 per panel: s0 s1 s2 s3 | b1 b2 b3 | m0 m1 | mid: begin trsm bcast applied | diag kernel done
   int np = 0;
   std::vector<cudaEvent_t> lev;   // triangular inverse: 5 per level (begin, gemm1, gemm2, gather, unpack)
   std::vector<int> lev_h;
@@ -86,7 +117,7 @@ struct ShardTrace {
   }
   void mark(int J, int k, cudaStream_t st) {
     if (!t0) return;
-    cudaEventRecord(ev[(size_t)J * 9 + k], st);
+    cudaEventRecord(ev[(size_t)J * 14 + k], st);
   }
 };
 inline ShardTrace& shard_trace() {
@@ -98,7 +129,7 @@ inline void shard_trace_begin(int NP, cudaStream_t st) {
   static const bool on = std::getenv("ACE_SHARD_TRACE") != nullptr;
   if (!on) return;
   if (!t.t0) cudaEventCreate(&t.t0);
-  while ((int)t.ev.size() < 9 * NP) {
+  while ((int)t.ev.size() < 14 * NP) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     t.ev.push_back(e);
@@ -113,13 +144,13 @@ inline void shard_trace_dump(int rank) {
   ShardTrace& t = shard_trace();
   if (!t.t0) return;
   cudaDeviceSynchronize();
-  std::fprintf(stderr, "[shard trace rank %d] J: factor_begin head_ready head_bcast diag_applied | bulk_trsm bulk_bcast la_applied | main_begin main_end (ms)\n", rank);
+  std::fprintf(stderr, "[shard trace rank %d] J: factor_begin head_ready head_bcast diag_applied | bulk_trsm bulk_bcast la_applied | main_begin main_end | mid_begin mid_trsm mid_bcast mid_applied | diag_kernel_done (ms)\n", rank);
   for (int J = 0; J < t.np; ++J) {
-    float v[9];
-    for (int k = 0; k < 9; ++k)
-      if (cudaEventElapsedTime(&v[k], t.t0, t.ev[(size_t)J * 9 + k]) != cudaSuccess) v[k] = -1.f;
-    std::fprintf(stderr, "[shard trace rank %d] %2d: %7.3f %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f | %7.3f %7.3f\n", rank, J, v[0],
-                 v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+    float v[14];
+    for (int k = 0; k < 14; ++k)
+      if (cudaEventElapsedTime(&v[k], t.t0, t.ev[(size_t)J * 14 + k]) != cudaSuccess) v[k] = -1.f;
+    std::fprintf(stderr, "[shard trace rank %d] %2d: %7.3f %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f | %7.3f %7.3f | %7.3f %7.3f %7.3f %7.3f | %7.3f\n",
+                 rank, J, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13]);
   }
   for (size_t l = 0; l < t.lev_h.size(); ++l) {
     float v[5];
@@ -190,6 +221,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     tr.mark(J, 0, w.side);
     if (mine) {
       ACE_TRY(diag_block_factor_invert(w, j0, j1, w.side, cx.world));  // L_JJ, X_JJ / U_JJ in place
+      tr.mark(J, 13, w.side);
       ACE_CUDA(cudaMemcpy2DAsync(Hd, sizeof(double) * hJ, blkptr(w, j0, j0), sizeof(double) * w.ld,
                                  sizeof(double) * wJ, (size_t)wJ, cudaMemcpyDeviceToDevice, w.side));
       if (wN > 0) {
@@ -200,7 +232,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
         t.B = blkptr(w, j0, j0); t.ldb = w.ld; t.b_tri = 2; t.Bdiag = w.DX + (size_t)j0 * TB * TB;
         t.C = Hd + wJ; t.ldc = hJ;
         t.M = (int)wN; t.N = (int)wJ; t.K = (int)wJ; t.alpha = 1.0; t.beta = 0.0;
-        ACE_TRY(launch_gemm_nt(t, w.side));
+        ACE_TRY(chain_gemm(t, cx.chain_ws, w.side));
       }
     }
     tr.mark(J, 1, w.side);
@@ -223,7 +255,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
       GemmNT g{};
       g.A = Hd + wJ; g.lda = hJ; g.B = Hd + wJ; g.ldb = hJ; g.C = blkptr(w, j1, j1); g.ldc = w.ld;
       g.M = (int)wN; g.N = (int)wN; g.K = (int)wJ; g.alpha = -1.0; g.beta = 1.0;
-      ACE_TRY(launch_gemm_nt(g, w.side));
+      ACE_TRY(chain_gemm(g, cx.chain_ws, w.side));
     }
     ACE_CUDA(cudaEventRecord(ev_diag[J], w.side));
     tr.mark(J, 3, w.side);
@@ -261,6 +293,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
     // ================= mid(J): rows [j2, j3), mid stream, communicator `comm3`
     if (use_mid) {
       ACE_CUDA(cudaStreamWaitEvent(mids, ev_head[J], 0));  // X_JJ (owner) / head data (look-ahead apply below)
+      tr.mark(J, 9, mids);
       if (wM > 0) {
         if (mine) {
           // these rows of my panel received panel J-1 with the rest of its bulk (and everything older before that)
@@ -272,7 +305,9 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
           t.M = (int)wM; t.N = (int)wJ; t.K = (int)wJ; t.alpha = 1.0; t.beta = 0.0;
           ACE_TRY(launch_gemm_nt(t, mids));
         }
+        tr.mark(J, 10, mids);
         if (!cx.emulate) ACE_NCCL(nc.Broadcast(Md, Md, (size_t)wM * wJ, ncclFloat64, J % cx.world, cx.comm3, mids));
+        tr.mark(J, 11, mids);
         if (la) {  // A[j2:j3, J+1] -= mid * Hn^T
           if (J >= 1) ACE_CUDA(cudaStreamWaitEvent(mids, ev_first[J - 1], 0));
           GemmNT g{};
@@ -282,6 +317,7 @@ inline int potrf_sharded(const DenseWork& w, const ShardCtx& cx) {
         }
       }
       ACE_CUDA(cudaEventRecord(ev_midla[J], mids));
+      tr.mark(J, 12, mids);
     }
     // ================= aux stream: the panel into this rank's A (the owner already has its diagonal block)
     ACE_CUDA(cudaStreamWaitEvent(w.aux, ev_head[J], 0));
