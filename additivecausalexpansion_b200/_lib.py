@@ -110,6 +110,8 @@ SIGNATURES = {
     "ace_ncs_basis_deriv": (_i, [_p, _i, _p, _i, _p]),
     "ace_normalize_train": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "ace_normalize_test": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ace_normalize_train_gpu": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "ace_normalize_test_gpu": (_i, [_p, _p, _i, _i, _i, _p]),
 }
 
 

@@ -208,26 +208,29 @@ def ncs_basis_deriv(x, knots):
     return out
 
 
-def normalize_train(y, X, Z):
+def normalize_train(y, X, Z, gpu=False):
     """src/utilities_cpp.cpp:13-104: y (n), X (n x px), Z (n x pz) are normalised IN PLACE (Fortran-ordered
-    float64 arrays required); returns the moments matrix."""
+    float64 arrays required); returns the moments matrix.  gpu=True: the device-side version (same results bit for
+    bit: csrc/prep_kernels.cuh)."""
     for a, nm in ((y, "y"), (X, "X"), (Z, "Z")):
         if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.f_contiguous):
             raise TypeError(f"{nm} must be a Fortran-contiguous float64 ndarray (normalised in place)")
     n, px = X.shape
     pz = Z.shape[1]
     mom = np.empty((1 + px + pz, 3), order="F")
-    check(lib().ace_normalize_train(_p(y), _p(X), _p(Z), n, px, pz, _p(mom)), "normalize_train")
+    fn = lib().ace_normalize_train_gpu if gpu else lib().ace_normalize_train
+    check(fn(_p(y), _p(X), _p(Z), n, px, pz, _p(mom)), "normalize_train")
     return mom
 
 
-def normalize_test(X, Z, moments):
-    """src/utilities_cpp.cpp:108-118 (in place)."""
+def normalize_test(X, Z, moments, gpu=False):
+    """src/utilities_cpp.cpp:108-118 (in place).  gpu=True: the device-side version."""
     for a, nm in ((X, "X"), (Z, "Z")):
         if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.f_contiguous):
             raise TypeError(f"{nm} must be a Fortran-contiguous float64 ndarray (normalised in place)")
     mom = _f(moments)
-    check(lib().ace_normalize_test(_p(X), _p(Z), X.shape[0], X.shape[1], Z.shape[1], _p(mom)), "normalize_test")
+    fn = lib().ace_normalize_test_gpu if gpu else lib().ace_normalize_test
+    check(fn(_p(X), _p(Z), X.shape[0], X.shape[1], Z.shape[1], _p(mom)), "normalize_test")
 
 
 # ----------------------------------------------------------------------------------------------- dense hooks

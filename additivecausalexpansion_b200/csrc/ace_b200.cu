@@ -23,6 +23,7 @@
 #include "grad3_kernel.cuh"
 #include "kernmat2_kernel.cuh"
 #include "pred_kernels.cuh"
+#include "prep_kernels.cuh"
 
 namespace ace {
 

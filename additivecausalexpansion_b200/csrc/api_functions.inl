@@ -677,3 +677,4 @@ int ace_bench_dense(int n, int reps, double* ms3) {
 }  // extern "C"
 
 #include "host_utils.inl"
+#include "prep_functions.inl"

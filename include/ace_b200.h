@@ -247,6 +247,11 @@ int ace_ncs_basis_deriv(const double* x, int n, const double* knots, int nknots,
  * moments: (1 + px + pz) x 3. */
 int ace_normalize_train(double* y, double* X, double* Z, int n, int px, int pz, double* moments);
 int ace_normalize_test(double* X, double* Z, int n, int px, int pz, const double* moments);
+/* The same two routines with the data resident on the device: column statistics by one
+ * bitonic sort per column, transforms as element-wise kernels, y moments with Armadillo's summation order --
+ * results identical to the host versions bit for bit.  Same arguments; need a CUDA device. */
+int ace_normalize_train_gpu(double* y, double* X, double* Z, int n, int px, int pz, double* moments);
+int ace_normalize_test_gpu(double* X, double* Z, int n, int px, int pz, const double* moments);
 
 #ifdef __cplusplus
 }
