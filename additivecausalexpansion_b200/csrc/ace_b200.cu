@@ -442,9 +442,14 @@ struct Core {
         ACE_TRY(head0.alloc(2 * pw * pw));
         ACE_TRY(head1.alloc(2 * pw * pw));
         if (!bulk) {
+          // priorities (numerically lower = more urgent): side (diagonal block, head) > mid > bulk > main (trailing
+          // updates); the bulk GEMMs are large, at the side stream's priority they would sit in front of the small
+          // kernels of the serial chain
           int lo = 0, hi = 0;
           ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-          ACE_CUDA(cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, hi));
+          int pb_ = (hi + lo) / 2;
+          if (const char* e = std::getenv("ACE_SHARD_BULK_PRIO")) pb_ = std::max(hi, std::min(lo, std::atoi(e)));
+          ACE_CUDA(cudaStreamCreateWithPriority(&bulk, cudaStreamNonBlocking, pb_));
         }
         {
           const char* sk = std::getenv("ACE_SHARD_SPLITK");
@@ -458,7 +463,7 @@ struct Core {
             if (!mids) {
               int lo = 0, hi = 0;
               ACE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-              ACE_CUDA(cudaStreamCreateWithPriority(&mids, cudaStreamNonBlocking, hi));
+              ACE_CUDA(cudaStreamCreateWithPriority(&mids, cudaStreamNonBlocking, std::min(lo, hi + 1)));
             }
           }
         }
