@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libace_b200.so")
+# ACE_B200_LIB: load another build of the library (tuning experiments: make OUT=... EXTRA=...)
+SO_PATH = os.environ.get("ACE_B200_LIB") or os.path.join(_HERE, "libace_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ace_b200.h")
 

@@ -22,8 +22,13 @@ static __constant__ double cKB[G3_SIZE];
 namespace kb2 {
 constexpr int T = 64;        // tile edge
 constexpr int LDT = T + 1;   // staging tile stride
+#if defined(KB2_QC) && defined(KB2_GRP)  // tuning experiments (Makefile EXTRA)
+constexpr int qc(int) { return KB2_QC; }
+constexpr int grp(int) { return KB2_GRP; }
+#else
 constexpr int qc(int BX) { return BX <= 6 ? 4 : (BX <= 12 ? 2 : 1); }      // columns per step
-constexpr int grp(int BX) { return BX <= 6 ? 1 : (BX <= 12 ? 2 : 4); }     // terms per lock-step group
+constexpr int grp(int BX) { return BX <= 6 ? 1 : (BX <= 12 ? 3 : 4); }     // terms per lock-step group (measured: scripts/variant_time.py)
+#endif
 inline size_t smem_bytes(int p, int Bz, bool sym) {
   size_t d = (size_t)(2 * p + 4 * Bz) * T + (sym ? (size_t)T * LDT : 0);
   return d * 8 + 16;

@@ -12,6 +12,9 @@ namespace ace {
 namespace g3 {
 // terms per lock-step group: covers BX without (much) padding, 3..5 independent chains
 constexpr int group(int BX) {
+#if defined(G3_GRP)  // tuning experiments (Makefile EXTRA)
+  if (BX >= G3_GRP) return G3_GRP;
+#endif
   if (BX <= 5) return BX;
   int best = 4, waste = (BX + 3) / 4 * 4 - BX;
   const int cand[3] = {5, 3, 6};
