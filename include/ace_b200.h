@@ -153,8 +153,10 @@ int ace_fit_get_train_stats(ace_fit* fit, double* stats);
 /* Multi-GPU sharding of ONE fit over `world` GPUs of a node (one process per GPU).
  * Every phase of the iteration is split and every rank ends an iteration with bit-identical parameters:
  *   - Cholesky: right-looking over 512-wide column panels dealt cyclically (panel J to rank J mod world); the owner
- *     factors and inverts the diagonal block, solves the rows below and broadcasts the panel over NVLink in two
- *     pieces (head: what the next owner needs at once; bulk: the rest, on a second communicator);
+ *     factors and inverts the diagonal block, solves the rows below and broadcasts the panel over NVLink in three
+ *     pieces, each on its own stream and communicator (head: diagonal block + the next panel's rows, what the next
+ *     owner needs at once; mid: the first block of the rows below, sent early because the next head needs it; bulk:
+ *     everything below);
  *   - kernel build: a rank builds exactly the K columns of the panels it owns -- K itself is never exchanged;
  *   - triangular inverse: grown behind the panels per column owner + ONE all-gather (or, when the trailing updates
  *     dominate, a merge tree whose upper levels are split over the ranks with one all-gather per level);
