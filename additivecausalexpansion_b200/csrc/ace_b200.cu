@@ -888,8 +888,8 @@ void ace_fit_default_config(ace_fit_config* cfg) {
 
 int ace_fit_create(ace_fit** out, const double* y, const double* X, const double* Z, int n, int p, int Bz,
                    const double* parameters, const ace_fit_config* cfg) {
-  if (!out || !y || !X || !Z || !parameters || !cfg) return usage("ace_fit_create: null argument");
-  if (n < 1 || p < 1 || Bz < 1) return usage("ace_fit_create: need n >= 1, p >= 1, Bz >= 1");
+  if (!out || !y || !X || (Bz > 0 && !Z) || !parameters || !cfg) return usage("ace_fit_create: null argument");
+  if (n < 1 || p < 1 || Bz < 0) return usage("ace_fit_create: need n >= 1, p >= 1, Bz >= 0");
   *out = nullptr;
   ace_fit* f = new (std::nothrow) ace_fit();
   if (!f) return usage("out of host memory");
@@ -1356,7 +1356,7 @@ extern "C" {
 
 int ace_fit_predict(ace_fit* f, const double* X2, const double* Z2, int nx, double mean_y, double std_y,
                     double* map, double* ci, double* var) {
-  if (!f || !X2 || !Z2 || !map || !ci || !var || nx < 1) return usage("ace_fit_predict: bad argument");
+  if (!f || !X2 || (f->c.Bz > 0 && !Z2) || !map || !ci || !var || nx < 1) return usage("ace_fit_predict: bad argument");
   Core& c = f->c;
   ACE_CUDA(cudaSetDevice(c.device));
   // A sharded fit blocks the test points over the ranks (the factor is replicated, rows are independent);
@@ -1370,14 +1370,15 @@ int ace_fit_predict(ace_fit* f, const double* X2, const double* Z2, int nx, doub
   const int lo = r * chunk, cnt = std::max(0, std::min(nx, lo + chunk) - lo);
   DBuf<double> dX2, dZ2, dLZ2, Kx, kd, res;
   ACE_TRY(dX2.alloc((size_t)nx_all * c.p));
-  ACE_TRY(dZ2.alloc((size_t)nx_all * c.Bz));
-  ACE_TRY(dLZ2.alloc((size_t)nx_all * c.Bz));
+  ACE_TRY(dZ2.alloc((size_t)nx_all * std::max(c.Bz, 1)));
+  ACE_TRY(dLZ2.alloc((size_t)nx_all * std::max(c.Bz, 1)));
   ACE_TRY(Kx.alloc((size_t)chunk * c.n_pad));
   ACE_TRY(kd.alloc(chunk));
   ACE_TRY(res.alloc((size_t)2 * nx_all));  // [map of all ranks | var of all ranks]
   ACE_TRY(upload_matrix(dX2.p, nx_all, nx_all, X2, nx, c.p, c.st));
   ACE_TRY(upload_matrix(dZ2.p, nx_all, nx_all, Z2, nx, c.Bz, c.st));
-  logabs_kernel<<<(unsigned)(((size_t)nx_all * c.Bz + 255) / 256), 256, 0, c.st>>>(dZ2.p, dLZ2.p, (size_t)nx_all * c.Bz);
+  if (c.Bz > 0)
+    logabs_kernel<<<(unsigned)(((size_t)nx_all * c.Bz + 255) / 256), 256, 0, c.st>>>(dZ2.p, dLZ2.p, (size_t)nx_all * c.Bz);
   ACE_CUDA(cudaGetLastError());
   ACE_TRY(c.enqueue_prep());  // kernels built from the CURRENT parameters (R/kernel_SE_R6.R:78-79)
   KernArgs a{};

@@ -11,8 +11,9 @@ static int sync_stream(cudaStream_t st) {
 // kernel build on host data (rectangular or symmetric)
 static int kernmat_host(int kind, int sym, const double* X1, const double* X2, const double* Z1, const double* Z2,
                         int n1, int n2, int p, int Bz, const double* par, double* full, double* elements) {
-  if (!X1 || !X2 || !Z1 || !Z2 || !par || !full) return usage("kernmat: null argument");
-  if (n1 < 1 || n2 < 1 || p < 1 || Bz < 1) return usage("kernmat: bad dimensions");
+  // Bz = 0 (no treatment basis: the nuisance term alone, B = 1) is what the reference computes for a Z with no columns
+  if (!X1 || !X2 || (Bz > 0 && (!Z1 || !Z2)) || !par || !full) return usage("kernmat: null argument");
+  if (n1 < 1 || n2 < 1 || p < 1 || Bz < 0) return usage("kernmat: bad dimensions");
   Core c;
   ACE_TRY(c.init(g_device, n1, p, Bz, kind, false, false));
   const int B = Bz + 1;
@@ -23,11 +24,12 @@ static int kernmat_host(int kind, int sym, const double* X1, const double* X2, c
   const double *x2 = c.X.p, *z2 = c.Z.p, *lz2 = c.LZ.p;
   if (!sym) {
     ACE_TRY(dX2.alloc((size_t)n2p * p));
-    ACE_TRY(dZ2.alloc((size_t)n2p * Bz));
-    ACE_TRY(dLZ2.alloc((size_t)n2p * Bz));
+    ACE_TRY(dZ2.alloc((size_t)n2p * std::max(Bz, 1)));
+    ACE_TRY(dLZ2.alloc((size_t)n2p * std::max(Bz, 1)));
     ACE_TRY(upload_matrix(dX2.p, n2p, n2p, X2, n2, p, c.st));
     ACE_TRY(upload_matrix(dZ2.p, n2p, n2p, Z2, n2, Bz, c.st));
-    logabs_kernel<<<(unsigned)(((size_t)n2p * Bz + 255) / 256), 256, 0, c.st>>>(dZ2.p, dLZ2.p, (size_t)n2p * Bz);
+    if (Bz > 0)
+      logabs_kernel<<<(unsigned)(((size_t)n2p * Bz + 255) / 256), 256, 0, c.st>>>(dZ2.p, dLZ2.p, (size_t)n2p * Bz);
     ACE_CUDA(cudaGetLastError());
     x2 = dX2.p; z2 = dZ2.p; lz2 = dLZ2.p;
   }
@@ -52,8 +54,8 @@ static int kernmat_host(int kind, int sym, const double* X1, const double* X2, c
 static int grad_host(int kind, const double* y, const double* X, const double* Z, const double* invK,
                      const double* eigenval, const double* par, double* stats, unsigned B, double std_y, int n, int p,
                      double* gradients) {
-  if (!y || !X || !Z || !invK || !eigenval || !par || !gradients) return usage("grad: null argument");
-  if (n < 1 || p < 1 || B < 2) return usage("grad: bad dimensions");
+  if (!y || !X || (B > 1 && !Z) || !invK || !eigenval || !par || !gradients) return usage("grad: null argument");
+  if (n < 1 || p < 1 || B < 1) return usage("grad: bad dimensions");
   Core c;
   ACE_TRY(c.init(g_device, n, p, (int)B - 1, kind, false, true));
   DBuf<double> Kinv;
@@ -365,6 +367,7 @@ static int fit_predict_marginal(ace_fit* f, const double* X2, const double* Z2, 
                                 double std_y, double std_Z, int calculate_ate, double* map, double* ci, double* var,
                                 double* avg, const unsigned char* subsets, int S, double* avgS, int* counts) {
   if (!f || !X2 || !Z2 || !dZ2 || !map || !ci || !var || nx < 1) return usage("predict_marginal: bad argument");
+  if (f->c.Bz < 1) return usage("predict_marginal: the fit has no treatment basis (Bz = 0)");
   Core& c = f->c;
   ACE_CUDA(cudaSetDevice(c.device));
   const int nx_pad = round_up(nx, TB);
