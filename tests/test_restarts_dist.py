@@ -59,3 +59,25 @@ def test_run_restarts_gloo_world2():
 def test_run_restarts_single_process():
     res = restarts.run_restarts(3, lambda i: {"evidence": float(i)})
     assert [r["fit"] for r in res] == [0, 1, 2] and restarts.best_restart(res)["fit"] == 2
+
+
+def test_run_restarts_concurrent_threads():
+    """`concurrency` fits of a rank's share at a time (one host thread each): same results, same order."""
+    import threading
+    import time
+
+    seen, lock, active, peak = [], threading.Lock(), [0], [0]
+
+    def fit(i):
+        with lock:
+            active[0] += 1
+            peak[0] = max(peak[0], active[0])
+        time.sleep(0.02)
+        with lock:
+            active[0] -= 1
+            seen.append(i)
+        return {"evidence": float(-i)}
+
+    res = restarts.run_restarts(6, fit, concurrency=3)
+    assert [r["fit"] for r in res] == list(range(6)) and [r["evidence"] for r in res] == [-float(i) for i in range(6)]
+    assert peak[0] >= 2 and sorted(seen) == list(range(6))
